@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- training rays/sec of the EmerNeRF per-ray-batch hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+    python bench.py --impl reference ...                      (the reference's algorithm on host cores)
+
+A *step* is one training pass of the hot path over one 8192-ray synthetic Waymo-shape pixel batch
+(BASELINE.json configs[1] by default): proposal sampling -> field -> compositing -> rgb + sky losses
+-> backward -> Adam on the field (and, on the steps the reference's schedule asks for it, the proposal
+loss + proposal Adam).  Rays shard across ranks (weak scaling: 8192 rays per GPU); the only
+collective is the gradient all-reduce.
+
+One JSON line on stdout (rank 0): metric/value/unit/..., plus
+  e2e          same metric through the public API with HOST (pinned) input batches copied H2D inside
+               every step and the loss read back D2H
+  roofline     the dominant kernel of the step vs the measured peak in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (restatement of the reference, oracle/) timed on this box's host cores
+               on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "training rays/sec (8192-ray batch)"
+UNIT = "rays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="static", choices=["static", "dynamic", "flow", "flow_feat"])
+    ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step")
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--cpu-rays", type=int, default=256, help="rays in one CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-all", action="store_true", help="print the per-kernel time table of one step")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- losses (host glue)
+def pixel_losses(out, batch):
+    """rgb L2 (loss/base.py:83-146, l2, coef 1) + opacity-based sky loss (loss/base.py:149-185, coef
+    1e-3).  Consumers of the hot path's outputs; plain torch."""
+    rgb = ((out["rgb"] - batch["pixels"]) ** 2).mean()
+    op = out["opacity"].squeeze(-1).clamp(1e-6, 1 - 1e-6)
+    sky = torch.nn.functional.binary_cross_entropy(op, 1.0 - batch["sky_masks"]) * 1e-3
+    loss = rgb + sky
+    if "dino_feat" in out and "features" in batch:
+        loss = loss + 0.5 * ((out["dino_feat"] - batch["features"]) ** 2).mean()
+    ex = out["extras"]
+    if "dynamic_density" in ex:
+        loss = loss + 0.01 * ex["dynamic_density"].mean()
+    if "shadow_ratio" in out:
+        loss = loss + 0.01 * out["shadow_ratio"].mean()
+    if "forward_pred_backward_flow" in ex:
+        loss = loss + 0.01 * 0.5 * ((ex["forward_flow"].detach() + ex["forward_pred_backward_flow"]) ** 2
+                                    + (ex["backward_flow"].detach() + ex["backward_pred_forward_flow"]) ** 2).mean()
+    return loss
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- the B200 arm
+class Trainer:
+    def __init__(self, args, rank, world, device):
+        from emernerf_b200 import configs, synthetic
+        from emernerf_b200.third_party.nerfacc_prop_net import get_proposal_requires_grad_fn
+
+        self.args, self.rank, self.world, self.device = args, rank, world, device
+        self.cfg = configs.make_cfg(args.variant, num_samples=args.samples)
+        self.field, self.props, self.est, self.opt = configs.build_hot_path(self.cfg, device, table_std=0.3)
+        self.field.train(); self.est.train()
+        [p.train() for p in self.props]
+        self.req_fn = get_proposal_requires_grad_fn()
+        self.step_idx = 2000                     # steady state of the schedule (every ~6th call)
+        feats = args.variant == "flow_feat"
+        nt = self.cfg.data.num_timesteps
+        # 8 distinct batches per rank, cycled (device-resident and pinned-host copies)
+        self.host = [synthetic.pixel_batch(args.rays, nt, 3, seed=1000 * rank + i, features=feats, pin=True)
+                     for i in range(8)]
+        self.dev = [{k: v.to(device) for k, v in b.items()} for b in self.host]
+        self.h2d_bytes = synthetic.bytes_of(self.host[0])
+        self.params = [p for p in self.field.parameters()]
+        self.prop_params = [p for m in self.props for p in m.parameters()]
+
+    def allreduce(self, params):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+
+        grads = [p.grad for p in params if p.grad is not None]
+        for g in grads:                           # NCCL over NVLink; hash tables dominate (122 MB)
+            dist.all_reduce(g, op=dist.ReduceOp.AVG)
+
+    def step(self, i, from_host):
+        from emernerf_b200.radiance_fields.render_utils import render_rays
+
+        if from_host:
+            batch = {k: v.to(self.device, non_blocking=True) for k, v in self.host[i % 8].items()}
+        else:
+            batch = self.dev[i % 8]
+        prg = self.req_fn(self.step_idx)
+        self.step_idx += 1
+        out = render_rays(self.field, self.est, self.props, batch, self.cfg, proposal_requires_grad=prg)
+        if prg:
+            ploss = self.est.compute_loss(out["extras"]["trans"], 1024.0)
+            self.est.optimizer.zero_grad()
+            ploss.backward()
+            self.allreduce(self.prop_params)
+            self.est.optimizer.step()
+        loss = pixel_losses(out, batch)
+        self.opt.zero_grad()
+        (loss * 1024.0).backward()                # GradScaler(2**10).scale(loss), never unscaled (Q17)
+        self.allreduce(self.params)
+        self.opt.step()
+        return loss
+
+
+def timed(trainer, steps, from_host, sync):
+    import torch.distributed as dist
+
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    last = None
+    for i in range(steps):
+        last = trainer.step(i, from_host)
+        if from_host:
+            last = last.item()                    # D2H read of the step's result
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    if trainer.world > 1:
+        t = torch.tensor([ms], device=trainer.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def kernel_table(trainer, sync):
+    """Per-C-ABI-call device times of ONE step (CUDA events around every library launch)."""
+    from emernerf_b200 import _lib
+
+    rec = []
+    _lib.set_profile(lambda name, args: True, rec)
+    sync()
+    trainer.step(0, False)
+    sync()
+    _lib.set_profile(None, None)
+    table = {}
+    for name, tag, e0, e1 in rec:
+        d = table.setdefault((name, tag), [0, 0.0])
+        d[0] += 1
+        d[1] += e0.elapsed_time(e1)
+    return table
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from emernerf_b200 import _lib
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the B200 arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    _lib.load()
+    tr = Trainer(args, rank, world, device)
+    for i in range(args.warmup):
+        tr.step(i, False)
+    sync()
+
+    # dominant kernel of the step (by summed device time), then its live timing in the timed region
+    table = kernel_table(tr, sync)
+    by_name = {}
+    for (name, tag), (cnt, ms) in table.items():
+        by_name[(name, tag)] = ms
+    dom = max(by_name, key=by_name.get)
+    grid_keys = [k for k in by_name if k[0] == "emer_grid_fwd"]
+    grid_dom = max(grid_keys, key=by_name.get) if grid_keys else None
+    if args.profile_all and rank == 0:
+        tot = sum(by_name.values())
+        for k, v in sorted(by_name.items(), key=lambda kv: -kv[1]):
+            print(f"# {k[0]:26s} {k[1]:28s} n={table[k][0]:3d} {v:8.3f} ms {100 * v / tot:5.1f}%", file=sys.stderr)
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    rec = []
+    watch = {dom, grid_dom} - {None}
+    _lib.set_profile(lambda name, args_: (name, _lib.tag_of(name, args_)) in watch, rec)
+    launches0 = _lib.LAUNCHES
+    ms = timed(tr, args.steps, False, sync)
+    launches = _lib.LAUNCHES - launches0
+    _lib.set_profile(None, None)
+    clk = clocks.stop() if rank == 0 else None
+
+    e2e = None
+    if not args.no_e2e:
+        for i in range(2):
+            tr.step(i, True)
+        ms_e2e = timed(tr, args.steps, True, sync)
+        e2e = {"value": args.rays * world * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": tr.h2d_bytes, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    def live(key):
+        ts = [e0.elapsed_time(e1) for name, tag, e0, e1 in rec if (name, tag) == key]
+        return (sum(ts) / len(ts), len(ts)) if ts else (None, 0)
+
+    roof = None
+    if grid_dom is not None:
+        avg_ms, n_l = live(grid_dom)
+        nbytes = _lib.algorithmic_bytes(grid_dom[1])
+        ach = nbytes / (avg_ms / 1e3) / 1e9
+        roof = {"kernel": f"{grid_dom[0]}[{grid_dom[1]}]", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": avg_ms, "launches_timed": n_l,
+                "share_of_step": by_name[grid_dom] / sum(by_name.values())}
+    dom_ms, dom_n = live(dom)
+    line = {
+        "metric": METRIC, "value": args.rays * world * args.steps / (ms / 1e3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic Waymo-shape rays (3 cams, 640x960, 200 timesteps), random-init MLPs, N(0,0.3) tables",
+        "config": {"workload": f"BASELINE configs[{['static', 'dynamic', 'flow', 'flow_feat'].index(args.variant) + 1}]: "
+                               f"default_config {args.variant} field, {args.rays} rays x {args.samples} samples "
+                               f"per GPU, proposal samples [128, 64], fwd+bwd+Adam, proposal update every ~6th step",
+                   "rays_per_gpu": args.rays, "samples": args.samples, "parallelism": f"ray-sharded dp{world}",
+                   "l2": "no explicit flush: each step streams > 1 GB of tables+activations through the 126 MB L2"},
+        "gpu_launches": launches,
+        "dominant_kernel": {"name": f"{dom[0]}[{dom[1]}]", "share_of_step": by_name[dom] / sum(by_name.values()),
+                            "avg_launch_ms": dom_ms},
+        "roofline": roof, "clocks": clk,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, steps=2, warmup=1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- the CPU arm
+def cpu_baseline(args, steps, warmup):
+    """The oracle (CPU restatement of the reference's Python + tcnn/nerfacc stand-ins) run as a training
+    step on the host cores: same config and tables, a bounded sample of ``--cpu-rays`` rays."""
+    from emernerf_b200 import configs, synthetic
+    from oracle import adapters, hotpath
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = configs.make_cfg(args.variant, num_samples=args.samples)
+    field, props, _, _ = configs.build_hot_path(cfg, "cpu", table_std=0.3)
+    fsd = adapters.cpu_state_dict(field, requires_grad=True)
+    psd = [adapters.cpu_state_dict(p, requires_grad=False) for p in props]
+    fspec = adapters.spec_from_module(field)
+    pspec = [adapters.spec_from_module(p) for p in props]
+    leaves = [v for v in fsd.values() if v.requires_grad]
+    feats = args.variant == "flow_feat"
+
+    def one(i):
+        b = synthetic.pixel_batch(args.cpu_rays, cfg.data.num_timesteps, 3, seed=i, features=feats)
+        out, _ = hotpath.render_rays(fsd, fspec, psd, pspec, b, num_samples=args.samples,
+                                     prop_samples=cfg.nerf.propnet.num_samples_per_prop, near_plane=0.1,
+                                     far_plane=1000.0, training=True)
+        loss = pixel_losses(out, b)
+        torch.autograd.grad(loss * 1024.0, leaves, allow_unused=True)
+        return float(loss.detach())
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return {"value": args.cpu_rays * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} training steps (fwd+bwd, no optimizer) of {args.cpu_rays} rays x {args.samples} "
+                      f"samples, same tables/config, {dt:.1f} s", "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, steps=max(1, min(args.steps, 4)), warmup=max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic Waymo-shape rays",
+        "config": {"workload": f"default_config {args.variant} field, CPU oracle (reference Python restated; "
+                               f"tcnn/nerfacc restated), bounded sample of {args.cpu_rays} rays x {args.samples}"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

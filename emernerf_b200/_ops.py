@@ -1,0 +1,327 @@
+"""torch.autograd wrappers over the C ABI (include/emer_b200.h).
+
+Mirrors the calling conventions of the reference's binding shim
+(third_party/tcnn_modules.py:115-208,235-263): inputs are cast to fp32 and made contiguous here,
+``ctx.set_materialize_grads(False)``, ``None`` gradients for inputs that do not need one.  All
+tensors must live on a CUDA device -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .grid_desc import GridDesc
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+STOT_KINDS = {"uniform": 0, "lindisp": 1, "sqrt": 2, "log": 3, "uniform_lindisp": 4, "uniform_lindisp_0": 5}
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("emernerf_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows(t: Tensor, k: int) -> Tuple[Tensor, int]:
+    """View as [N, k] rows with unit inner stride; returns (2-D tensor, row stride)."""
+    t2 = t.reshape(-1, k)
+    if t2.dtype != torch.float32:
+        t2 = t2.to(torch.float32)
+    if t2.stride(1) != 1 or (t2.shape[0] > 1 and t2.stride(0) < k):
+        t2 = t2.contiguous()
+    return t2, (t2.stride(0) if t2.shape[0] > 1 else k)
+
+
+# ----------------------------------------------------------------------------- hash grid
+class _GridEncode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, params: Tensor, desc: GridDesc):
+        ctx.set_materialize_grads(False)
+        _need_cuda(x, params)
+        x = _f32c(x)
+        params = _f32c(params)
+        n = x.shape[0]
+        y = torch.empty((n, desc.n_output_dims), dtype=torch.float32, device=x.device)
+        _lib.call("emer_grid_fwd", ctypes.byref(desc.c), _ptr(x), _ptr(params), _ptr(y), n, _stream())
+        ctx.save_for_backward(x, params)
+        ctx.desc = desc
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy is None:
+            return None, None, None
+        x, params = ctx.saved_tensors
+        desc = ctx.desc
+        dy = _f32c(dy)
+        need_x, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dparams = torch.zeros_like(params) if need_p else None
+        dx = torch.empty_like(x) if need_x else None
+        if need_x or need_p:
+            _lib.call("emer_grid_bwd", ctypes.byref(desc.c), _ptr(x), _ptr(params), _ptr(dy), _ptr(dparams),
+                      _ptr(dx), x.shape[0], _stream())
+        return dx, dparams, None
+
+
+def grid_encode(x: Tensor, params: Tensor, desc: GridDesc) -> Tensor:
+    """[N, D] -> [N, L*F] multi-resolution hash-grid features."""
+    if x.dim() != 2 or x.shape[1] != desc.n_dims:
+        raise ValueError(f"grid_encode expects [N, {desc.n_dims}], got {tuple(x.shape)}")
+    if params.numel() != desc.n_params:
+        raise ValueError(f"grid params have {params.numel()} floats, level table needs {desc.n_params}")
+    return _GridEncode.apply(x, params, desc)
+
+
+@torch.no_grad()
+def grid_indices(x: Tensor, desc: GridDesc) -> Tensor:
+    _need_cuda(x)
+    x = _f32c(x)
+    out = torch.empty((x.shape[0], desc.n_levels, 2 ** desc.n_dims), dtype=torch.int32, device=x.device)
+    _lib.call("emer_grid_indices", ctypes.byref(desc.c), _ptr(x), _ptr(out), x.shape[0], _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- contraction
+class _Contract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos: Tensor, aabb: Tensor, time: Optional[Tensor], unbounded: bool, selector: bool = True):
+        ctx.set_materialize_grads(False)
+        _need_cuda(pos, aabb)
+        pos = _f32c(pos)
+        aabb = _f32c(aabb.reshape(-1))
+        n = pos.shape[0]
+        out_dim = 3 if time is None else 4
+        ctx.time_shape = None if time is None else time.shape
+        if time is not None:
+            time = _f32c(time.reshape(-1))
+            if time.shape[0] != n:
+                raise ValueError("time must have one value per point")
+        out = torch.empty((n, out_dim), dtype=torch.float32, device=pos.device)
+        _lib.call("emer_contract_fwd", _ptr(pos), _ptr(aabb), _ptr(time), _ptr(out), out_dim, int(unbounded), int(selector),
+                  n, _stream())
+        ctx.save_for_backward(pos, aabb)
+        ctx.out_dim, ctx.unbounded, ctx.selector = out_dim, bool(unbounded), bool(selector)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if dout is None:
+            return None, None, None, None, None
+        pos, aabb = ctx.saved_tensors
+        dout = _f32c(dout)
+        need_pos = ctx.needs_input_grad[0]
+        need_t = ctx.out_dim == 4 and ctx.needs_input_grad[2]
+        if not (need_pos or need_t):
+            return None, None, None, None, None
+        dpos = torch.empty_like(pos)
+        dtime = torch.empty(pos.shape[0], dtype=torch.float32, device=pos.device) if need_t else None
+        _lib.call("emer_contract_bwd", _ptr(pos), _ptr(aabb), _ptr(dout), _ptr(dpos), _ptr(dtime), ctx.out_dim,
+                  int(ctx.unbounded), int(ctx.selector), pos.shape[0], _stream())
+        if dtime is not None:
+            dtime = dtime.view(ctx.time_shape)
+        return (dpos if need_pos else None), None, dtime, None, None
+
+
+def contract(pos: Tensor, aabb: Tensor, time: Optional[Tensor] = None, unbounded: bool = True) -> Tensor:
+    """[N,3] world positions -> [N,3] (or [N,4] with the time column) grid coordinates in [0,1]."""
+    return _Contract.apply(pos, aabb, time, unbounded, True)
+
+
+def contract_raw(pos: Tensor, aabb: Tensor) -> Tensor:
+    """The bare inf-norm contraction of nerf_utils.py:13-28 (no in-cube selector)."""
+    return _Contract.apply(pos, aabb, None, True, False)
+
+
+# ----------------------------------------------------------------------------- trunc_exp(x - 1)
+class _TruncExpM1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor):
+        _need_cuda(x)
+        shape = x.shape
+        x2 = _f32c(x).reshape(-1)
+        y = torch.empty_like(x2)
+        _lib.call("emer_trunc_exp_fwd", _ptr(x2), 1, _ptr(y), x2.numel(), _stream())
+        ctx.save_for_backward(x2)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2,) = ctx.saved_tensors
+        dy2 = _f32c(dy).reshape(-1)
+        dx = torch.empty_like(x2)
+        _lib.call("emer_trunc_exp_bwd", _ptr(x2), 1, _ptr(dy2), _ptr(dx), x2.numel(), _stream())
+        return dx.view(dy.shape)
+
+
+def density_activation(x: Tensor) -> Tensor:
+    """trunc_exp(x - 1): exp forward, exp(clamp(.,15)) backward (nerf_utils.py:59-75)."""
+    return _TruncExpM1.apply(x)
+
+
+# ----------------------------------------------------------------------------- dense layers
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Optional[Tensor], act: int):
+        ctx.set_materialize_grads(False)
+        _need_cuda(x, w)
+        n_out, k = w.shape
+        lead = x.shape[:-1]
+        x2, ldx = _rows(x, k)
+        w = _f32c(w)
+        bb = None if b is None else _f32c(b)
+        n = x2.shape[0]
+        y = torch.empty((n, n_out), dtype=torch.float32, device=x.device)
+        _lib.call("emer_linear_fwd", _ptr(x2), ldx, _ptr(w), _ptr(bb), _ptr(y), n_out, n, k, n_out, act, _stream())
+        ctx.save_for_backward(x2, w, y if act != ACT_NONE else None)
+        ctx.act, ctx.ldx, ctx.x_shape, ctx.has_bias = act, ldx, x.shape, b is not None
+        return y.view(*lead, n_out)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy is None:
+            return None, None, None, None
+        x2, w, y = ctx.saved_tensors
+        n_out, k = w.shape
+        n = x2.shape[0]
+        dy2, lddy = _rows(dy, n_out)
+        dx = dw = db = None
+        st = _stream()
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n, k), dtype=torch.float32, device=dy.device)
+            _lib.call("emer_linear_bwd_data", _ptr(dy2), lddy, _ptr(y), n_out, ctx.act, _ptr(w), _ptr(dx), k, n, k,
+                      n_out, 0, st)
+            dx = dx.view(ctx.x_shape)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros_like(w)
+            db = torch.zeros(n_out, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            _lib.call("emer_linear_bwd_weight", _ptr(x2), ctx.ldx, _ptr(dy2), lddy, _ptr(y), n_out, ctx.act,
+                      _ptr(dw), _ptr(db), n, k, n_out, st)
+        return dx, dw, db, None
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
+    """act(x @ w.T + b) over the last dimension."""
+    if x.shape[-1] != w.shape[1]:
+        raise ValueError(f"linear: input width {x.shape[-1]} != weight width {w.shape[1]}")
+    return _Linear.apply(x, w, b, act)
+
+
+# ----------------------------------------------------------------------------- sampling
+@torch.no_grad()
+def pdf_resample(vals: Tensor, cdfs: Tensor, n: int, bias: Optional[Tensor], s_min: float, s_max: float,
+                 kind: str, want_bins: bool = False):
+    """Inverse-CDF resampling of [R, m1] edges into n intervals; returns (s_edges, t_edges[, bins])."""
+    _need_cuda(vals, cdfs)
+    vals, cdfs = _f32c(vals), _f32c(cdfs)
+    r, m1 = cdfs.shape
+    out_s = torch.empty((r, n + 1), dtype=torch.float32, device=vals.device)
+    out_t = torch.empty_like(out_s)
+    bins = torch.empty((r, n + 1), dtype=torch.int32, device=vals.device) if want_bins else None
+    if bias is not None:
+        bias = _f32c(bias.reshape(-1))
+        if bias.shape[0] != r:
+            raise ValueError("bias must have one value per ray")
+    _lib.call("emer_pdf_resample", _ptr(vals), _ptr(cdfs), m1, n, _ptr(bias), float(s_min), float(s_max),
+              STOT_KINDS[kind], _ptr(out_s), _ptr(out_t), _ptr(bins), r, _stream())
+    return (out_s, out_t, bins) if want_bins else (out_s, out_t)
+
+
+# ----------------------------------------------------------------------------- volume rendering
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t0: Tensor, t1: Tensor, sigma: Tensor, want_cdf: bool):
+        _need_cuda(t0, t1, sigma)
+        t0, t1, sigma = _f32c(t0), _f32c(t1), _f32c(sigma)
+        r, s = sigma.shape
+        dev = sigma.device
+        weights = torch.empty((r, s), dtype=torch.float32, device=dev)
+        trans = torch.empty_like(weights)
+        opacity = torch.empty((r, 1), dtype=torch.float32, device=dev)
+        depth = torch.empty_like(opacity)
+        median = torch.empty_like(opacity)
+        cdf = torch.empty((r, s + 1), dtype=torch.float32, device=dev) if want_cdf else None
+        _lib.call("emer_composite_fwd", _ptr(t0), _ptr(t1), _ptr(sigma), _ptr(weights), _ptr(trans), _ptr(opacity),
+                  _ptr(depth), _ptr(median), _ptr(cdf), r, s, _stream())
+        ctx.save_for_backward(t0, t1, sigma, weights, trans)
+        ctx.mark_non_differentiable(median)
+        if cdf is None:
+            cdf = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(cdf)
+        ctx.want_cdf = want_cdf
+        return weights, trans, opacity, depth, median, cdf
+
+    @staticmethod
+    def backward(ctx, g_w, g_t, g_o, g_d, _g_m, g_cdf):
+        t0, t1, sigma, weights, trans = ctx.saved_tensors
+        r, s = sigma.shape
+        if ctx.want_cdf and g_cdf is not None:
+            # cdf[:, :S] = 1 - trans  ->  d trans -= g_cdf[:, :S]
+            extra = -g_cdf[:, :s]
+            g_t = extra if g_t is None else g_t + extra
+        if g_w is None and g_t is None and g_o is None and g_d is None:
+            return None, None, None, None
+        c = lambda g: None if g is None else _f32c(g)
+        g_w, g_t, g_o, g_d = c(g_w), c(g_t), c(g_o), c(g_d)
+        dsigma = torch.empty_like(sigma)
+        _lib.call("emer_composite_bwd", _ptr(t0), _ptr(t1), _ptr(sigma), _ptr(weights), _ptr(trans), _ptr(g_w),
+                  _ptr(g_t), _ptr(g_o), _ptr(g_d), _ptr(dsigma), r, s, _stream())
+        return None, None, dsigma, None
+
+
+def composite(t0: Tensor, t1: Tensor, sigma: Tensor, want_cdf: bool = False):
+    """weights, trans [R,S]; opacity, depth, median_depth [R,1]; cdf [R,S+1] (or an empty tensor)."""
+    return _Composite.apply(t0, t1, sigma, want_cdf)
+
+
+class _Accumulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w: Tensor, v: Tensor):
+        ctx.set_materialize_grads(False)
+        _need_cuda(w, v)
+        w, v = _f32c(w), _f32c(v)
+        r, s = w.shape
+        c = v.shape[-1]
+        out = torch.empty((r, c), dtype=torch.float32, device=w.device)
+        _lib.call("emer_accumulate_fwd", _ptr(w), _ptr(v), _ptr(out), r, s, c, _stream())
+        ctx.save_for_backward(w, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None:
+            return None, None
+        w, v = ctx.saved_tensors
+        r, s = w.shape
+        c = v.shape[-1]
+        g = _f32c(g)
+        dw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        dv = torch.empty_like(v) if ctx.needs_input_grad[1] else None
+        _lib.call("emer_accumulate_bwd", _ptr(w), _ptr(v), _ptr(g), _ptr(dw), _ptr(dv), r, s, c, _stream())
+        return dw, dv
+
+
+def accumulate(w: Tensor, v: Tensor) -> Tensor:
+    """sum_s w[R,S] * v[R,S,C] -> [R,C]."""
+    if v.dim() == 2:
+        v = v.unsqueeze(-1)
+    if v.shape[:2] != w.shape:
+        raise ValueError(f"accumulate: weights {tuple(w.shape)} vs values {tuple(v.shape)}")
+    return _Accumulate.apply(w, v)

@@ -1,0 +1,131 @@
+/*
+ * emer_b200 -- C ABI of the B200-native EmerNeRF hot path (libemer_b200.so, sm_100a only).
+ *
+ * This is the drop-in boundary.  The reference reaches its native code through two Python
+ * FFIs: the tiny-cuda-nn pybind object (third_party/tcnn_modules.py:102,122,161,216-219) and
+ * nerfacc's `_C` extension (third_party/nerfacc_prop_net.py:11-14,153,172;
+ * radiance_fields/render_utils.py:4-8).  Every entry point below names the reference call it
+ * replaces.  The fused entry points (emer_mlp_*, emer_composite_*) replace chains of torch
+ * library calls on the same path (radiance_fields/mlp.py:38-46, radiance_field.py:74-198,
+ * render_utils.py:73-115).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers into caller-owned (PyTorch caching-allocator) memory,
+ *     fp32 unless noted, dense row-major; the library allocates nothing on the hot path
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, re-entrant per stream,
+ *     and never synchronise the host
+ *   - return 0 on success; on failure a negative code, with emer_last_error() giving the text.
+ *     No exceptions cross the boundary.  Shape/dtype/contiguity are validated by the caller
+ *     (emernerf_b200/_ops.py), mirroring third_party/tcnn_modules.py:236-262.
+ */
+#ifndef EMER_B200_H
+#define EMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMER_MAX_LEVELS 16
+
+/* Level table of one multi-resolution grid (host struct, passed by pointer, copied per launch).
+ * Replaces the opaque object returned by _C.create_encoding(n_input_dims, encoding_config,
+ * precision) -- third_party/tcnn_modules.py:420-423.  Filled by emernerf_b200/grid_desc.py with
+ * tiny-cuda-nn's level formulas (scale_l = exp2(l*log2(per_level_scale))*base - 1,
+ * res_l = ceil(scale_l)+1, size_l = min(round_up(res^D, 8), 2^log2_hashmap_size)). */
+typedef struct emer_grid_desc {
+    int32_t n_dims;                          /* 3 or 4 */
+    int32_t n_levels;                        /* 1..16 */
+    int32_t n_feat;                          /* 1, 2 or 4 floats per entry */
+    int32_t reserved;
+    float scale[EMER_MAX_LEVELS];
+    uint32_t resolution[EMER_MAX_LEVELS];
+    uint32_t offset[EMER_MAX_LEVELS + 1];    /* in entries; level l owns [offset[l], offset[l+1]) */
+    uint32_t hashed[EMER_MAX_LEVELS];        /* 1: coherent-prime hash, 0: dense stride index */
+} emer_grid_desc;
+
+const char* emer_last_error(void);
+int emer_version(void);
+
+/* ---- multi-resolution hash grid (replaces native_tcnn_module.fwd / .bwd,
+ *      third_party/tcnn_modules.py:122,161) ------------------------------------------------- */
+/* y[N, L*F] = encode(x[N, D]); feature index = level*F + f. */
+int emer_grid_fwd(const emer_grid_desc* g, const float* x, const float* table, float* y,
+                  int64_t n, void* stream);
+/* dtable (same layout as table, ACCUMULATED with atomics -- caller zeroes) and/or dx[N, D];
+ * either may be NULL. */
+int emer_grid_bwd(const emer_grid_desc* g, const float* x, const float* table, const float* dy,
+                  float* dtable, float* dx, int64_t n, void* stream);
+/* test hook: corner entry indices [N, L, 2^D] (int32, absolute entry index) -- the "bit-exact
+ * sample indices" check of BASELINE.json. */
+int emer_grid_indices(const emer_grid_desc* g, const float* x, int32_t* idx, int64_t n, void* stream);
+
+/* ---- scene contraction (radiance_fields/nerf_utils.py:13-28 + the 0/1 selector of
+ *      radiance_field.py:294-300,834-835) ----------------------------------------------------- */
+/* out[N, out_dim] (out_dim 3 or 4): columns 0..2 = contracted*selector; column 3 = time[N]
+ * (broadcast per point) when out_dim == 4.  unbounded=0 -> plain aabb normalisation.
+ * apply_selector=0 gives the bare `contract()` of nerf_utils.py (no zeroing of outside points). */
+int emer_contract_fwd(const float* pos, const float* aabb6, const float* time, float* out,
+                      int out_dim, int unbounded, int apply_selector, int64_t n, void* stream);
+/* dpos[N,3] = J^T dout[:, 0:3] (selector and time carry no gradient to pos; dtime_or_null[N]
+ * receives dout[:,3]). */
+int emer_contract_bwd(const float* pos, const float* aabb6, const float* dout, float* dpos,
+                      float* dtime, int out_dim, int unbounded, int apply_selector, int64_t n,
+                      void* stream);
+
+/* ---- density activation trunc_exp(x - 1) (radiance_fields/nerf_utils.py:59-75,
+ *      radiance_field.py:28,794).  x has row stride ldx (reads column 0). ------------------- */
+int emer_trunc_exp_fwd(const float* x, int64_t ldx, float* y, int64_t n, void* stream);
+int emer_trunc_exp_bwd(const float* x, int64_t ldx, const float* dy, float* dx, int64_t n, void* stream);
+
+/* ---- dense layers of the MLP heads (replaces cuBLAS SGEMM under nn.Linear:
+ *      radiance_fields/mlp.py:38-46, radiance_field.py:74-198,808-812) ---------------------- */
+enum { EMER_ACT_NONE = 0, EMER_ACT_RELU = 1, EMER_ACT_SIGMOID = 2 };
+/* Y[N, n_out] = act(X[N, k] W[n_out, k]^T + b) */
+int emer_linear_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y,
+                    int64_t ldy, int64_t n, int k, int n_out, int act, void* stream);
+/* dZ = dY * act'(Y);  dX[N, k] (=|+=) dZ W */
+int emer_linear_bwd_data(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act,
+                         const float* w, float* dx, int64_t lddx, int64_t n, int k, int n_out,
+                         int accumulate, void* stream);
+/* dW[n_out, k] += dZ^T X;  db[n_out] += sum_rows dZ   (atomics; caller zeroes) */
+int emer_linear_bwd_weight(const float* x, int64_t ldx, const float* dy, int64_t lddy,
+                           const float* y, int64_t ldy, int act, float* dw, float* db,
+                           int64_t n, int k, int n_out, void* stream);
+
+/* ---- inverse-CDF resampling (replaces nerfacc.pdf.importance_sampling + _transform_stot,
+ *      third_party/nerfacc_prop_net.py:153-160,172-175,299-339) ---------------------------- */
+enum { EMER_STOT_UNIFORM = 0, EMER_STOT_LINDISP = 1, EMER_STOT_SQRT = 2, EMER_STOT_LOG = 3,
+       EMER_STOT_UNIFORM_LINDISP = 4, EMER_STOT_UNIFORM_LINDISP_0 = 5 };
+/* vals, cdfs: [R, m1]; out_s, out_t: [R, n+1]; out_bins (int32 [R, n+1], may be NULL) = the
+ * upper-bound index p of each output edge.  bias: [R] stratified jitter in [0,1) or NULL (0.5).
+ * s_min/s_max are the fp32 contract_fn(near/far) values computed by the caller. */
+int emer_pdf_resample(const float* vals, const float* cdfs, int m1, int n, const float* bias,
+                      float s_min, float s_max, int stot_kind, float* out_s, float* out_t,
+                      int32_t* out_bins, int64_t n_rays, void* stream);
+
+/* ---- volume rendering along rays (replaces nerfacc.render_transmittance_from_density /
+ *      render_weight_from_density / accumulate_along_rays and the torch cumsum/searchsorted of
+ *      radiance_fields/render_utils.py:73-115) ---------------------------------------------- */
+/* per ray, S samples: weights, trans [R,S]; opacity (clamped to [1e-6,1]), depth, median_depth [R];
+ * cdf_or_null [R, S+1] = 1 - cat(trans, 0) (nerfacc_prop_net.py:165-168). */
+int emer_composite_fwd(const float* t0, const float* t1, const float* sigma, float* weights,
+                       float* trans, float* opacity, float* depth, float* median_depth,
+                       float* cdf, int64_t n_rays, int n_samples, void* stream);
+/* dsigma[R,S] from any of g_weights, g_trans [R,S], g_opacity, g_depth [R] (NULL = zero). */
+int emer_composite_bwd(const float* t0, const float* t1, const float* sigma, const float* weights,
+                       const float* trans, const float* g_weights, const float* g_trans,
+                       const float* g_opacity, const float* g_depth, float* dsigma,
+                       int64_t n_rays, int n_samples, void* stream);
+/* out[R, C] = sum_s w[R,S] * v[R,S,C] */
+int emer_accumulate_fwd(const float* w, const float* v, float* out, int64_t n_rays, int n_samples,
+                        int c, void* stream);
+/* dw[R,S] (may be NULL) = sum_c g[R,C] v[R,S,C];  dv[R,S,C] (may be NULL) = w * g */
+int emer_accumulate_bwd(const float* w, const float* v, const float* g, float* dw, float* dv,
+                        int64_t n_rays, int n_samples, int c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMER_B200_H */

@@ -1,0 +1,298 @@
+"""Kernel-level parity (through the C ABI) against the CPU oracle: integer work bit-exact, fp32
+within the tolerance written at each check."""
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import hotpath, nerfacc_ref as nf, tcnn_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+GRIDS = {
+    "3d_f4": (3, (4, 8, 64, 10, 4)),          # dense + hashed levels
+    "4d_f4": (4, (4, 4, 32, 10, 4)),
+    "3d_f1": (3, (4, 16, 96, 12, 1)),
+    "4d_f2": (4, (3, 4, 24, 9, 2)),
+    "3d_f4_cfg": (3, (10, 16, 8192, 20, 4)),   # configs/default_config.yaml static grid (indices only)
+    "4d_f4_cfg": (4, (10, 32, 8192, 18, 4)),
+}
+
+
+def _grid(name):
+    from emernerf_b200.grid_desc import GridDesc
+
+    D, args = GRIDS[name]
+    cfg = hotpath.hash_encoder_config(*args)
+    return D, GridDesc(D, cfg), tcnn_ref.grid_geometry(D, cfg)
+
+
+def _points(n, D, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, D, generator=g)
+    x[: n // 8, :3] = 0.0               # rejected points are encoded at the origin (Q2)
+    x[n // 8: n // 4] = torch.rand(n // 4 - n // 8, D, generator=g).round()   # exact corners 0/1
+    if D == 4:
+        x[-5:, 3] = 1.0                 # t = 1 is a legal timestamp
+    return x
+
+
+@pytest.mark.parametrize("name", list(GRIDS))
+def test_grid_corner_indices_bit_exact(name):
+    from emernerf_b200 import _ops
+
+    D, desc, geom = _grid(name)
+    x = _points(4096, D)
+    got = _ops.grid_indices(x.to(DEV), desc).cpu().long()
+    for lvl in range(geom.n_levels):
+        want, _, _, _ = tcnn_ref.corner_indices_and_weights(x, geom, lvl)
+        assert torch.equal(got[:, lvl, :], want), f"level {lvl}"
+
+
+@pytest.mark.parametrize("name", ["3d_f4", "4d_f4", "3d_f1", "4d_f2"])
+def test_grid_forward_backward_vs_oracle(name):
+    from emernerf_b200 import _ops
+
+    D, desc, geom = _grid(name)
+    g = torch.Generator().manual_seed(1)
+    x = _points(3000, D, seed=3)
+    params = torch.randn(geom.n_params, generator=g)
+    dy = torch.randn(3000, geom.n_output_dims, generator=g)
+
+    xo = x.clone().requires_grad_(True)
+    po = params.clone().requires_grad_(True)
+    yo = tcnn_ref.grid_forward(xo, po, geom)
+    yo.backward(dy)
+
+    xg = x.to(DEV).requires_grad_(True)
+    pg = params.to(DEV).requires_grad_(True)
+    yg = _ops.grid_encode(xg, pg, desc)
+    yg.backward(dy.to(DEV))
+    # forward: same fma chain as the oracle -> equal up to the oracle's double-rounding emulation
+    assert (yg.cpu() - yo).abs().max().item() <= 1e-6 * yo.abs().max().item()
+    assert (yg.cpu() == yo).float().mean().item() > 0.999
+    # table gradient: atomics reorder the fp32 sums
+    assert rel_err(pg.grad, po.grad) < 2e-5
+    # input gradient (dy/dx through the interpolation weights, tcnn semantics)
+    assert rel_err(xg.grad, xo.grad) < 2e-5
+
+
+def test_grid_full_size_properties():
+    """BASELINE config size (8192 x 64 points, 10x4 levels, 2^20 table): properties that do not need
+    the oracle -- partition of unity, linearity in the table, and the adjoint identity
+    <dy, enc_T(x)> == <grad_T, T> that ties backward to forward."""
+    from emernerf_b200 import _ops
+
+    _, desc, _ = _grid("3d_f4_cfg")
+    n = 8192 * 64
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.rand(n, 3, device=DEV, generator=g)
+    ones = torch.ones(desc.n_params, device=DEV)
+    y1 = _ops.grid_encode(x, ones, desc)
+    assert (y1 - 1).abs().max().item() < 1e-5
+    t1 = torch.randn(desc.n_params, device=DEV, generator=g)
+    t2 = torch.randn(desc.n_params, device=DEV, generator=g)
+    lin = _ops.grid_encode(x, 0.5 * t1 - 2.0 * t2, desc)
+    ref = 0.5 * _ops.grid_encode(x, t1, desc) - 2.0 * _ops.grid_encode(x, t2, desc)
+    assert (lin - ref).abs().max().item() < 2e-5
+    tp = t1.clone().requires_grad_(True)
+    y = _ops.grid_encode(x, tp, desc)
+    dy = torch.randn(y.shape, device=DEV, generator=g)
+    y.backward(dy)
+    lhs = (dy.double() * y.detach().double()).sum()
+    rhs = (tp.grad.double() * t1.double()).sum()
+    assert abs(lhs - rhs).item() <= 1e-4 * abs(lhs).item() + 1e-2
+
+
+def test_grid_empty_and_ragged_batches():
+    from emernerf_b200 import _ops
+
+    D, desc, geom = _grid("3d_f4")
+    p = torch.randn(geom.n_params)
+    assert _ops.grid_encode(torch.empty(0, 3, device=DEV), p.to(DEV), desc).shape == (0, geom.n_output_dims)
+    for n in (1, 31, 257):
+        x = torch.rand(n, 3)
+        assert rel_err(_ops.grid_encode(x.to(DEV), p.to(DEV), desc), tcnn_ref.grid_forward(x, p, geom)) < 1e-6
+
+
+def test_contract_forward_backward_vs_oracle():
+    from emernerf_b200 import _ops
+
+    g = torch.Generator().manual_seed(0)
+    aabb = torch.tensor([-20.0, -40.0, 0.0, 80.0, 40.0, 20.0])
+    pos = torch.randn(5000, 3, generator=g) * torch.tensor([200.0, 150.0, 40.0]) + torch.tensor([30.0, 0.0, 10.0])
+    pos[:500] = torch.rand(500, 3, generator=g) * torch.tensor([100.0, 80.0, 20.0]) + torch.tensor([-20.0, -40.0, 0.0])
+    t = torch.rand(5000, generator=g)
+    for unbounded in (True, False):
+        po = pos.clone().requires_grad_(True)
+        yo = hotpath.contract_points(po, aabb, unbounded)
+        w = torch.randn(5000, 3, generator=g)
+        (yo * w).sum().backward()
+        pg = pos.to(DEV).requires_grad_(True)
+        yg = _ops.contract(pg, aabb.to(DEV), None, unbounded)
+        (yg * w.to(DEV)).sum().backward()
+        assert torch.equal(yg.cpu(), yo.detach()), "contraction is per-op rounded like torch: bit exact"
+        assert rel_err(pg.grad, po.grad) < 1e-5
+    y4 = _ops.contract(pos.to(DEV), aabb.to(DEV), t.to(DEV), True)
+    assert torch.equal(y4[:, 3].cpu(), t) and torch.equal(y4[:, :3].cpu(), hotpath.contract_points(pos, aabb, True))
+    raw = _ops.contract_raw(pos.to(DEV), aabb.to(DEV)).cpu()
+    assert torch.equal(raw, hotpath.contract(pos, aabb))
+
+
+@pytest.mark.parametrize("k,n_out,act", [(40, 64, 1), (64, 128, 0), (113, 64, 1), (177, 64, 1), (64, 3, 2),
+                                        (8, 64, 1), (64, 1, 0), (64, 6, 0), (49, 64, 1), (32, 64, 0)])
+def test_linear_forward_backward_vs_fp32_reference(k, n_out, act):
+    """Plain PyTorch fp32 (CPU) reference of the same layer; tolerance 2e-5 relative (fp32 sums of up
+    to 177 terms in a different order)."""
+    from emernerf_b200 import _ops
+
+    g = torch.Generator().manual_seed(k * 131 + n_out)
+    n = 1000 + k
+    x = torch.randn(n, k, generator=g)
+    w = torch.randn(n_out, k, generator=g) / k ** 0.5
+    b = torch.randn(n_out, generator=g)
+    dy = torch.randn(n, n_out, generator=g)
+    xo, wo, bo = (t.clone().requires_grad_(True) for t in (x, w, b))
+    z = torch.nn.functional.linear(xo, wo, bo)
+    yo = torch.relu(z) if act == 1 else (torch.sigmoid(z) if act == 2 else z)
+    yo.backward(dy)
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    yg = _ops.linear(xg, wg, bg, act)
+    yg.backward(dy.to(DEV))
+    assert rel_err(yg, yo) < 2e-5
+    assert rel_err(xg.grad, xo.grad) < 2e-5
+    assert rel_err(wg.grad, wo.grad) < 5e-5
+    assert rel_err(bg.grad, bo.grad) < 5e-5
+
+
+def test_linear_strided_input_rows():
+    from emernerf_b200 import _ops
+
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn(777, 128, generator=g)
+    w = torch.randn(64, 64, generator=g)
+    b = torch.randn(64, generator=g)
+    fg = full.to(DEV).requires_grad_(True)
+    y = _ops.linear(fg[:, 64:], w.to(DEV), b.to(DEV), 1)
+    fo = full.clone().requires_grad_(True)
+    yo = torch.relu(torch.nn.functional.linear(fo[:, 64:], w, b))
+    y.sum().backward(); yo.sum().backward()
+    assert rel_err(y, yo) < 2e-5 and rel_err(fg.grad, fo.grad) < 2e-5
+
+
+@pytest.mark.parametrize("m1,n", [(2, 128), (129, 64), (65, 64), (33, 16), (17, 7)])
+@pytest.mark.parametrize("stratified", [False, True])
+def test_pdf_resample_bit_exact(m1, n, stratified):
+    """Identical CDFs in -> bit-identical bins, s edges and t edges out (BASELINE: 'bit-exact sample
+    indices and ray offsets')."""
+    from emernerf_b200 import _ops
+
+    g = torch.Generator().manual_seed(m1 * 7 + n)
+    R = 513
+    if m1 == 2:
+        vals = torch.tensor([[0.0, 1.0]]).repeat(R, 1)
+        cdfs = vals.clone()
+    else:
+        vals = torch.sort(torch.rand(R, m1, generator=g), -1).values
+        w = torch.rand(R, m1 - 1, generator=g) ** 4
+        w[:, ::5] = 0.0                       # flat CDF stretches (du < 1e-10 branch)
+        cdfs = torch.cat([torch.zeros(R, 1), torch.cumsum(w / w.sum(-1, keepdim=True), -1)], -1)
+        cdfs[:, -1] = 1.0
+    jit = torch.rand(R, 1, generator=g) if stratified else None
+    s_min, s_max = hotpath.s_bounds("uniform_lindisp", 0.1, 1000.0)
+    bias = jit if stratified else torch.full((R, 1), 0.5)
+    _, p0, p1 = nf.importance_sampling_bins(cdfs, n, bias)
+    iv, _ = nf.importance_sampling(nf.RayIntervals(vals), cdfs, n, stratified, jitter=jit)
+    t_want = hotpath._s_to_t("uniform_lindisp", iv.vals, 0.1, 1000.0)
+    s_got, t_got, bins = _ops.pdf_resample(vals.to(DEV), cdfs.to(DEV), n, None if jit is None else jit.to(DEV),
+                                           s_min, s_max, "uniform_lindisp", want_bins=True)
+    bins = bins.cpu().long()
+    assert torch.equal((bins - 1).clamp(0, m1 - 1), p0) and torch.equal(bins.clamp(0, m1 - 1), p1)
+    assert torch.equal(s_got.cpu(), iv.vals)
+    assert torch.equal(t_got.cpu(), t_want)
+    assert (s_got[:, 1:] >= s_got[:, :-1]).all()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lindisp", "sqrt", "uniform_lindisp_0"])
+def test_pdf_resample_other_warps(kind):
+    from emernerf_b200 import _ops
+
+    R, n = 64, 32
+    vals = torch.tensor([[0.0, 1.0]]).repeat(R, 1)
+    s_min, s_max = hotpath.s_bounds(kind, 0.5, 100.0)
+    iv, _ = nf.importance_sampling(nf.RayIntervals(vals), vals.clone(), n, False)
+    want = hotpath._s_to_t(kind, iv.vals, 0.5, 100.0)
+    _, t = _ops.pdf_resample(vals.to(DEV), vals.to(DEV), n, None, s_min, s_max, kind)
+    assert torch.equal(t.cpu(), want)
+
+
+@pytest.mark.parametrize("S", [64, 128, 16, 45, 1])
+def test_composite_forward_backward_vs_oracle(S):
+    from emernerf_b200 import _ops
+
+    g = torch.Generator().manual_seed(S)
+    R = 300
+    edges = torch.sort(torch.rand(R, S + 1, generator=g) * 50, -1).values
+    t0, t1 = edges[:, :-1].contiguous(), edges[:, 1:].contiguous()
+    sigma = torch.rand(R, S, generator=g) ** 3 * 2
+    sigma[:10] = 0.0                                          # empty rays: opacity clamps at 1e-6
+    sigma[10:20] *= 50                                        # saturating rays
+    so = sigma.clone().requires_grad_(True)
+    trans, alphas = nf.render_transmittance_from_density(t0, t1, so)
+    w = trans * alphas
+    op = nf.accumulate_along_rays(w, None).clamp(1e-6, 1.0)
+    mid = (t0 + t1)[..., None] / 2.0
+    dep = nf.accumulate_along_rays(w, mid) / op
+    cw = torch.cumsum(w, -1)
+    mi = torch.searchsorted(cw, torch.full((R, 1), 0.5), side="left").clamp(0, S - 1)
+    med = torch.gather(mid[..., 0], -1, mi)
+    gw, gt = torch.randn(R, S, generator=g), torch.randn(R, S, generator=g)
+    go, gd = torch.randn(R, 1, generator=g), torch.randn(R, 1, generator=g) * 0.1
+    cdf_o = 1.0 - torch.cat([trans, torch.zeros_like(trans[..., :1])], -1)
+    gc = torch.randn(R, S + 1, generator=g)
+    ((w * gw).sum() + (trans * gt).sum() + (op * go).sum() + (dep * gd).sum() + (cdf_o * gc).sum()).backward()
+
+    sg = sigma.to(DEV).requires_grad_(True)
+    W, T, O, D, M, C = _ops.composite(t0.to(DEV), t1.to(DEV), sg, want_cdf=True)
+    ((W * gw.to(DEV)).sum() + (T * gt.to(DEV)).sum() + (O * go.to(DEV)).sum() + (D * gd.to(DEV)).sum()
+     + (C * gc.to(DEV)).sum()).backward()
+    tol = 1e-5       # expf differs by ulps between host and device; scan order differs from cumsum
+    assert rel_err(W, w) < tol and rel_err(T, trans) < tol and rel_err(O, op) < tol and rel_err(D, dep) < tol
+    assert rel_err(C, cdf_o) < tol
+    agree = (M.cpu() == med).float().mean().item()
+    assert agree > 0.98, agree                                # median index flips only at cw ~= 0.5 ties
+    assert rel_err(sg.grad, so.grad) < 5e-5
+    # telescoping identity: sum of weights == 1 - T_end*(1 - alpha_end)
+    assert torch.allclose(W.sum(-1), 1 - T[:, -1] * torch.exp(-(sg.detach()[:, -1] * (t1 - t0).to(DEV)[:, -1])), atol=1e-5)
+
+
+@pytest.mark.parametrize("C", [1, 3, 6, 64])
+def test_accumulate_forward_backward(C):
+    from emernerf_b200 import _ops
+
+    g = torch.Generator().manual_seed(C)
+    R, S = 257, 64
+    w = torch.rand(R, S, generator=g)
+    v = torch.randn(R, S, C, generator=g)
+    go = torch.randn(R, C, generator=g)
+    wo, vo = w.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    nf.accumulate_along_rays(wo, vo).backward(go)
+    wg, vg = w.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    out = _ops.accumulate(wg, vg)
+    out.backward(go.to(DEV))
+    assert rel_err(out, nf.accumulate_along_rays(w, v)) < 1e-5
+    assert rel_err(wg.grad, wo.grad) < 1e-5 and rel_err(vg.grad, vo.grad) < 1e-6
+
+
+def test_trunc_exp():
+    from emernerf_b200 import _ops
+
+    x = torch.linspace(-20, 25, 1001)
+    xo = x.clone().requires_grad_(True)
+    hotpath.density_activation(xo).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    y = _ops.density_activation(xg)
+    y.sum().backward()
+    assert rel_err(y, hotpath.density_activation(x)) < 1e-6
+    assert torch.allclose(xg.grad.cpu(), xo.grad, rtol=2e-6)
+    assert xg.grad.max().item() <= float(torch.exp(torch.tensor(15.0))) * (1 + 1e-6)     # clamped backward
