@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-all", action="store_true", help="print the per-kernel time table of one step")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying "
+                    "the captured CUDA graphs of the step")
     return ap.parse_args()
 
 
@@ -120,7 +122,9 @@ class Trainer:
 
         self.args, self.rank, self.world, self.device = args, rank, world, device
         self.cfg = configs.make_cfg(args.variant, num_samples=args.samples)
-        self.field, self.props, self.est, self.opt = configs.build_hot_path(self.cfg, device, table_std=0.3)
+        self.use_graph = not args.no_graph
+        self.field, self.props, self.est, self.opt = configs.build_hot_path(self.cfg, device, table_std=0.3,
+                                                                            capturable=self.use_graph)
         self.field.train(); self.est.train()
         [p.train() for p in self.props]
         self.req_fn = get_proposal_requires_grad_fn()
@@ -144,15 +148,49 @@ class Trainer:
         for g in grads:                           # NCCL over NVLink; hash tables dominate (122 MB)
             dist.all_reduce(g, op=dist.ReduceOp.AVG)
 
-    def step(self, i, from_host):
-        from emernerf_b200.radiance_fields.render_utils import render_rays
+    # ---- CUDA graphs: the step is ~10^2 small launches; capture it once per schedule branch
+    def build_graphs(self):
+        self.static = {k: torch.empty_like(v) for k, v in self.dev[0].items()}
+        self.graphs, self.static_loss = {}, {}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for prg in (False, True, False):
+                self._step_body(self.static, prg)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from emernerf_b200 import _lib
 
+        self.graph_launches = {}
+        for prg in (False, True):
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.LAUNCHES
+            with torch.cuda.graph(g):
+                self.static_loss[prg] = self._step_body(self.static, prg)
+            self.graph_launches[prg] = _lib.LAUNCHES - n0      # library kernels inside this graph
+            self.graphs[prg] = g
+
+    def step(self, i, from_host):
+        prg = self.req_fn(self.step_idx)
+        self.step_idx += 1
+        if self.use_graph and not getattr(self, "_profiling", False):
+            if not hasattr(self, "graphs"):
+                self.build_graphs()
+            src = self.host[i % 8] if from_host else self.dev[i % 8]
+            for k, v in self.static.items():
+                v.copy_(src[k], non_blocking=True)
+            self.graphs[prg].replay()
+            self.replayed_launches = getattr(self, "replayed_launches", 0) + self.graph_launches[prg]
+            return self.static_loss[prg]
         if from_host:
             batch = {k: v.to(self.device, non_blocking=True) for k, v in self.host[i % 8].items()}
         else:
             batch = self.dev[i % 8]
-        prg = self.req_fn(self.step_idx)
-        self.step_idx += 1
+        return self._step_body(batch, prg)
+
+    def _step_body(self, batch, prg):
+        from emernerf_b200.radiance_fields.render_utils import render_rays
+
         out = render_rays(self.field, self.est, self.props, batch, self.cfg, proposal_requires_grad=prg)
         if prg:
             ploss = self.est.compute_loss(out["extras"]["trans"], 1024.0)
@@ -189,16 +227,21 @@ def timed(trainer, steps, from_host, sync):
     return ms
 
 
-def kernel_table(trainer, sync):
-    """Per-C-ABI-call device times of ONE step (CUDA events around every library launch)."""
+def kernel_table(trainer, sync, steps=3):
+    """Device time of every library launch (CUDA events on the launching stream, eager launches) over
+    ``steps`` training steps.  Returns {(name, shape_tag): [launches, total_ms]}."""
     from emernerf_b200 import _lib
 
     rec = []
-    _lib.set_profile(lambda name, args: True, rec)
+    trainer._profiling = True              # eager launches: events cannot be timed inside a replayed graph
+    trainer.step(0, False)                 # one untimed eager step (allocator warm-up)
     sync()
-    trainer.step(0, False)
+    _lib.set_profile(lambda name, args: True, rec)
+    for i in range(steps):
+        trainer.step(i, False)
     sync()
     _lib.set_profile(None, None)
+    trainer._profiling = False
     table = {}
     for name, tag, e0, e1 in rec:
         d = table.setdefault((name, tag), [0, 0.0])
@@ -234,29 +277,13 @@ def run_ours(args):
         tr.step(i, False)
     sync()
 
-    # dominant kernel of the step (by summed device time), then its live timing in the timed region
-    table = kernel_table(tr, sync)
-    by_name = {}
-    for (name, tag), (cnt, ms) in table.items():
-        by_name[(name, tag)] = ms
-    dom = max(by_name, key=by_name.get)
-    grid_keys = [k for k in by_name if k[0] == "emer_grid_fwd"]
-    grid_dom = max(grid_keys, key=by_name.get) if grid_keys else None
-    if args.profile_all and rank == 0:
-        tot = sum(by_name.values())
-        for k, v in sorted(by_name.items(), key=lambda kv: -kv[1]):
-            print(f"# {k[0]:26s} {k[1]:28s} n={table[k][0]:3d} {v:8.3f} ms {100 * v / tot:5.1f}%", file=sys.stderr)
-
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    rec = []
-    watch = {dom, grid_dom} - {None}
-    _lib.set_profile(lambda name, args_: (name, _lib.tag_of(name, args_)) in watch, rec)
     launches0 = _lib.LAUNCHES
+    tr.replayed_launches = 0
     ms = timed(tr, args.steps, False, sync)
-    launches = _lib.LAUNCHES - launches0
-    _lib.set_profile(None, None)
+    launches = (_lib.LAUNCHES - launches0) + tr.replayed_launches
     clk = clocks.stop() if rank == 0 else None
 
     e2e = None
@@ -267,6 +294,11 @@ def run_ours(args):
         e2e = {"value": args.rays * world * args.steps / (ms_e2e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": tr.h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}
+
+    # per-kernel device times: CUDA events around every library launch over 3 eager steps, same
+    # process / inputs / clocks, right after the timed region (a replayed graph cannot be event-timed
+    # per kernel).  The ncu launch list under profiles/ must agree on the kernel's SHARE.
+    table = kernel_table(tr, sync, steps=3)          # every rank runs it (the steps all-reduce)
 
     if rank != 0:
         if world > 1:
@@ -280,20 +312,30 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
-    def live(key):
-        ts = [e0.elapsed_time(e1) for name, tag, e0, e1 in rec if (name, tag) == key]
-        return (sum(ts) / len(ts), len(ts)) if ts else (None, 0)
+    tot_ms = sum(v[1] for v in table.values())
+    per_launch = {k: v[1] / v[0] for k, v in table.items()}
+    dom = max(table, key=lambda k: table[k][1])
+    grid_keys = [k for k in table if k[0] == "emer_grid_fwd"]
+    grid_dom = max(grid_keys, key=lambda k: table[k][1]) if grid_keys else None
+    if args.profile_all:
+        for k, v in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            print(f"# {k[0]:26s} {k[1]:32s} n={v[0]:3d} {v[1] / 3:8.3f} ms/step {100 * v[1] / tot_ms:5.1f}%",
+                  file=sys.stderr)
+        print(f"# library kernels: {tot_ms / 3:.3f} ms/step of {ms / args.steps:.3f} ms/step", file=sys.stderr)
 
     roof = None
     if grid_dom is not None:
-        avg_ms, n_l = live(grid_dom)
+        avg_ms = per_launch[grid_dom]
         nbytes = _lib.algorithmic_bytes(grid_dom[1])
         ach = nbytes / (avg_ms / 1e3) / 1e9
         roof = {"kernel": f"{grid_dom[0]}[{grid_dom[1]}]", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                 "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": avg_ms, "launches_timed": n_l,
-                "share_of_step": by_name[grid_dom] / sum(by_name.values())}
-    dom_ms, dom_n = live(dom)
+                "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": avg_ms,
+                "launches_timed": table[grid_dom][0],
+                "share_of_library_kernel_time": table[grid_dom][1] / tot_ms,
+                "timing": "CUDA events around each launch, 3 eager steps after the timed region"}
+    dom_ms = per_launch[dom]
+    by_name = {k: v[1] for k, v in table.items()}
     line = {
         "metric": METRIC, "value": args.rays * world * args.steps / (ms / 1e3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -305,8 +347,10 @@ def run_ours(args):
                    "rays_per_gpu": args.rays, "samples": args.samples, "parallelism": f"ray-sharded dp{world}",
                    "l2": "no explicit flush: each step streams > 1 GB of tables+activations through the 126 MB L2"},
         "gpu_launches": launches,
-        "dominant_kernel": {"name": f"{dom[0]}[{dom[1]}]", "share_of_step": by_name[dom] / sum(by_name.values()),
+        "dominant_kernel": {"name": f"{dom[0]}[{dom[1]}]", "share_of_library_kernel_time": by_name[dom] / tot_ms,
                             "avg_launch_ms": dom_ms},
+        "cuda_graph": tr.use_graph,
+        "library_kernel_ms_per_step": tot_ms / 3,
         "roofline": roof, "clocks": clk,
     }
     if e2e is not None:
@@ -325,7 +369,9 @@ def cpu_baseline(args, steps, warmup):
     from emernerf_b200 import configs, synthetic
     from oracle import adapters, hotpath
 
-    cores = os.cpu_count() or 1
+    # torch's intra-op pool gets SLOWER beyond ~16-32 threads on these small ops (measured: 128
+    # threads -> 107 s/step vs 1.2 s/step on 8); use what helps and report the count actually used
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     cfg = configs.make_cfg(args.variant, num_samples=args.samples)
     field, props, _, _ = configs.build_hot_path(cfg, "cpu", table_std=0.3)

@@ -76,7 +76,7 @@ def tag_of(name: str, args) -> str:
     try:
         if name in ("emer_grid_fwd", "emer_grid_bwd"):
             g = args[0]._obj
-            n = args[4] if name == "emer_grid_fwd" else args[7]
+            n = args[4] if name == "emer_grid_fwd" else args[6]
             extra = ""
             if name == "emer_grid_bwd":
                 extra = ("_T" if args[4].value else "") + ("_X" if args[5].value else "")

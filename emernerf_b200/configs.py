@@ -55,7 +55,7 @@ def make_cfg(variant: str = "static", num_timesteps: int = 200, num_cams: int = 
               variant=variant)
 
 
-def build_hot_path(cfg: NS, device="cuda", table_std: float = 0.0, seed: int = 0):
+def build_hot_path(cfg: NS, device="cuda", table_std: float = 0.0, seed: int = 0, capturable: bool = False):
     """(field, proposal_networks, estimator, optimizer) as builders.py builds them.  ``table_std > 0``
     replaces tcnn's degenerate U(-1e-4, 1e-4) table init by N(0, table_std) ("trained-like" state for
     bandwidth measurements)."""
@@ -87,6 +87,8 @@ def build_hot_path(cfg: NS, device="cuda", table_std: float = 0.0, seed: int = 0
     field = field.to(device)
     props = [p.to(device) for p in props]
     adam = dict(lr=cfg.optim.lr, eps=1e-15, weight_decay=cfg.optim.weight_decay, betas=(0.9, 0.99))
+    if capturable:                      # CUDA-graph capture of the optimizer step
+        adam["capturable"] = True
     prop_opt = torch.optim.Adam(itertools.chain(*[p.parameters() for p in props]), **adam)
     est = PropNetEstimator(prop_opt, None,
                            enable_anti_aliasing_loss=cfg.nerf.propnet.enable_anti_aliasing_level_loss,

@@ -21,7 +21,8 @@ __device__ __forceinline__ float s_to_t(float s, float s_min, float s_max, int k
         case EMER_STOT_LINDISP: return 1.0f / v;
         case EMER_STOT_SQRT: return v * v;
         case EMER_STOT_LOG: return expf(v);
-        case EMER_STOT_UNIFORM_LINDISP: return v < 0.5f ? v * 400.0f : 200.0f / (2.0f - 2.0f * v);
+        // torch evaluates `200 / x` as reciprocal(x) * 200 (Tensor.__rtruediv__): two roundings
+        case EMER_STOT_UNIFORM_LINDISP: return v < 0.5f ? v * 400.0f : (1.0f / (2.0f - 2.0f * v)) * 200.0f;
         default: return v < 0.5f ? 2.0f * v : 1.0f / (2.0f - 2.0f * v);
     }
 }
