@@ -16,7 +16,15 @@ from torch import Tensor
 from . import _lib
 from .grid_desc import GridDesc
 
+import os
+
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+# Dense layers run on the tcgen05 tensor-core kernels (3xTF32, fp32-accurate).  "simt" selects the
+# fp32 CUDA-core kernels of linear_simt.cu (the bit-faithful checker); both are sm_100a code in the
+# same library -- this is a debugging switch, not a backend dispatch.
+LINEAR_IMPL = os.environ.get("EMER_LINEAR", "tc")
+LINEAR_WGRAD_IMPL = os.environ.get("EMER_LINEAR_WGRAD", "tc")
+TC_MIN_ROWS = 1024          # tiny per-ray heads are launch-bound either way
 STOT_KINDS = {"uniform": 0, "lindisp": 1, "sqrt": 2, "log": 3, "uniform_lindisp": 4, "uniform_lindisp_0": 5}
 
 
@@ -189,9 +197,11 @@ class _Linear(torch.autograd.Function):
         bb = None if b is None else _f32c(b)
         n = x2.shape[0]
         y = torch.empty((n, n_out), dtype=torch.float32, device=x.device)
-        _lib.call("emer_linear_fwd", _ptr(x2), ldx, _ptr(w), _ptr(bb), _ptr(y), n_out, n, k, n_out, act, _stream())
+        use_tc = LINEAR_IMPL == "tc" and n >= TC_MIN_ROWS and k <= 256 and n_out <= 256
+        _lib.call("emer_linear_tc_fwd" if use_tc else "emer_linear_fwd", _ptr(x2), ldx, _ptr(w), _ptr(bb), _ptr(y),
+                  n_out, n, k, n_out, act, _stream())
         ctx.save_for_backward(x2, w, y if act != ACT_NONE else None)
-        ctx.act, ctx.ldx, ctx.x_shape, ctx.has_bias = act, ldx, x.shape, b is not None
+        ctx.act, ctx.ldx, ctx.x_shape, ctx.has_bias, ctx.use_tc = act, ldx, x.shape, b is not None, use_tc
         return y.view(*lead, n_out)
 
     @staticmethod
@@ -206,13 +216,14 @@ class _Linear(torch.autograd.Function):
         st = _stream()
         if ctx.needs_input_grad[0]:
             dx = torch.empty((n, k), dtype=torch.float32, device=dy.device)
-            _lib.call("emer_linear_bwd_data", _ptr(dy2), lddy, _ptr(y), n_out, ctx.act, _ptr(w), _ptr(dx), k, n, k,
+            _lib.call("emer_linear_tc_bwd_data" if ctx.use_tc else "emer_linear_bwd_data", _ptr(dy2), lddy, _ptr(y), n_out, ctx.act, _ptr(w), _ptr(dx), k, n, k,
                       n_out, 0, st)
             dx = dx.view(ctx.x_shape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.zeros_like(w)
             db = torch.zeros(n_out, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-            _lib.call("emer_linear_bwd_weight", _ptr(x2), ctx.ldx, _ptr(dy2), lddy, _ptr(y), n_out, ctx.act,
+            tc_w = ctx.use_tc and LINEAR_WGRAD_IMPL == "tc" and n_out <= 128
+            _lib.call("emer_linear_tc_bwd_weight" if tc_w else "emer_linear_bwd_weight", _ptr(x2), ctx.ldx, _ptr(dy2), lddy, _ptr(y), n_out, ctx.act,
                       _ptr(dw), _ptr(db), n, k, n_out, st)
         return dx, dw, db, None
 

@@ -94,6 +94,20 @@ int emer_linear_bwd_weight(const float* x, int64_t ldx, const float* dy, int64_t
                            const float* y, int64_t ldy, int act, float* dw, float* db,
                            int64_t n, int k, int n_out, void* stream);
 
+/* Same contracts on the tcgen05 tensor cores: fp32 operands split into tf32 hi+lo, three
+ * tcgen05.mma.kind::tf32 per k-step accumulate A_lo*B_hi + A_hi*B_lo + A_hi*B_hi in TMEM
+ * (fp32-accurate "3xTF32"; see emernerf_b200/csrc/linear_tc.cu).  Widths: k, n_out <= 256. */
+int emer_linear_tc_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y,
+                       int64_t ldy, int64_t n, int k, int n_out, int act, void* stream);
+int emer_linear_tc_bwd_data(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act,
+                            const float* w, float* dx, int64_t lddx, int64_t n, int k, int n_out,
+                            int accumulate, void* stream);
+/* dW[n_out, k] += dZ^T X, db += column sums of dZ; dW^T accumulates in TMEM across the CTA's row
+ * tiles (MN-major operands), flushed once with atomics.  k <= 256, n_out <= 128. */
+int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const float* dy, int64_t lddy,
+                              const float* y, int64_t ldy, int act, float* dw, float* db,
+                              int64_t n, int k, int n_out, void* stream);
+
 /* ---- inverse-CDF resampling (replaces nerfacc.pdf.importance_sampling + _transform_stot,
  *      third_party/nerfacc_prop_net.py:153-160,172-175,299-339) ---------------------------- */
 enum { EMER_STOT_UNIFORM = 0, EMER_STOT_LINDISP = 1, EMER_STOT_SQRT = 2, EMER_STOT_LOG = 3,

@@ -139,15 +139,18 @@ def test_contract_forward_backward_vs_oracle():
     assert torch.equal(raw, hotpath.contract(pos, aabb))
 
 
+@pytest.mark.parametrize("impl", ["tc", "simt"])
 @pytest.mark.parametrize("k,n_out,act", [(40, 64, 1), (64, 128, 0), (113, 64, 1), (177, 64, 1), (64, 3, 2),
-                                        (8, 64, 1), (64, 1, 0), (64, 6, 0), (49, 64, 1), (32, 64, 0)])
-def test_linear_forward_backward_vs_fp32_reference(k, n_out, act):
+                                        (8, 64, 1), (64, 1, 0), (64, 6, 0), (49, 64, 1), (32, 64, 0),
+                                        (116, 64, 1), (180, 64, 1), (40, 192, 0)])
+def test_linear_forward_backward_vs_fp32_reference(k, n_out, act, impl, monkeypatch):
     """Plain PyTorch fp32 (CPU) reference of the same layer; tolerance 2e-5 relative (fp32 sums of up
-    to 177 terms in a different order)."""
+    to 180 terms in a different order).  ``tc`` = tcgen05 3xTF32 kernels, ``simt`` = FFMA kernels."""
     from emernerf_b200 import _ops
 
+    monkeypatch.setattr(_ops, "LINEAR_IMPL", impl)
     g = torch.Generator().manual_seed(k * 131 + n_out)
-    n = 1000 + k
+    n = 3000 + k
     x = torch.randn(n, k, generator=g)
     w = torch.randn(n_out, k, generator=g) / k ** 0.5
     b = torch.randn(n_out, generator=g)
@@ -165,11 +168,13 @@ def test_linear_forward_backward_vs_fp32_reference(k, n_out, act):
     assert rel_err(bg.grad, bo.grad) < 5e-5
 
 
-def test_linear_strided_input_rows():
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_linear_strided_input_rows(impl, monkeypatch):
     from emernerf_b200 import _ops
 
+    monkeypatch.setattr(_ops, "LINEAR_IMPL", impl)
     g = torch.Generator().manual_seed(5)
-    full = torch.randn(777, 128, generator=g)
+    full = torch.randn(2777, 128, generator=g)
     w = torch.randn(64, 64, generator=g)
     b = torch.randn(64, generator=g)
     fg = full.to(DEV).requires_grad_(True)
@@ -178,6 +183,41 @@ def test_linear_strided_input_rows():
     yo = torch.relu(torch.nn.functional.linear(fo[:, 64:], w, b))
     y.sum().backward(); yo.sum().backward()
     assert rel_err(y, yo) < 2e-5 and rel_err(fg.grad, fo.grad) < 2e-5
+
+
+def test_linear_wgrad_tc_matches_simt(monkeypatch):
+    """tcgen05 weight gradient (dW^T accumulated in TMEM over many row tiles) vs the FFMA kernel."""
+    from emernerf_b200 import _ops
+
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for k, n_out, act in ((177, 64, 1), (64, 128, 0), (40, 64, 1), (64, 3, 2)):
+        n = 64 * 1500 + 21
+        x = torch.randn(n, k, device=DEV, generator=g)
+        w = (torch.randn(n_out, k, device=DEV, generator=g) / k ** 0.5)
+        b = torch.randn(n_out, device=DEV, generator=g)
+        dy = torch.randn(n, n_out, device=DEV, generator=g)
+        grads = {}
+        for impl in ("tc", "simt"):
+            monkeypatch.setattr(_ops, "LINEAR_WGRAD_IMPL", impl)
+            wp, bp = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            _ops.linear(x, wp, bp, act).backward(dy)
+            grads[impl] = (wp.grad, bp.grad)
+        assert rel_err(grads["tc"][0], grads["simt"][0]) < 2e-5, (k, n_out)
+        assert rel_err(grads["tc"][1], grads["simt"][1]) < 2e-5, (k, n_out)
+
+
+def test_linear_tc_many_tiles_and_ragged_tail():
+    """More tiles than CTAs (persistent loop, ring phases wrap) and a ragged last tile."""
+    from emernerf_b200 import _ops
+
+    g = torch.Generator(device=DEV).manual_seed(11)
+    n = 128 * 700 + 37
+    x = torch.randn(n, 64, device=DEV, generator=g)
+    w = torch.randn(64, 64, device=DEV, generator=g) / 8
+    b = torch.randn(64, device=DEV, generator=g)
+    y = _ops.linear(x, w, b, 1)
+    ref = torch.relu(x.double() @ w.double().t() + b.double()).float()
+    assert rel_err(y, ref) < 5e-6
 
 
 @pytest.mark.parametrize("m1,n", [(2, 128), (129, 64), (65, 64), (33, 16), (17, 7)])
