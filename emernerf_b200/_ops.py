@@ -185,54 +185,187 @@ def density_activation(x: Tensor) -> Tensor:
 
 
 # ----------------------------------------------------------------------------- dense layers
-class _Linear(torch.autograd.Function):
+def _pad4(v: int) -> int:
+    return (v + 3) // 4 * 4
+
+
+def _tc_rows_ok(n: int, k: int, n_out: int) -> bool:
+    return LINEAR_IMPL == "tc" and n >= TC_MIN_ROWS and k <= 256 and n_out <= 256
+
+
+def _aligned(t: Tensor, ld: int) -> bool:
+    return ld % 4 == 0 and t.data_ptr() % 16 == 0
+
+
+def _layer_fwd(x2: Tensor, ldx: int, w: Tensor, b: Optional[Tensor], y: Tensor, ldy: int, n: int, act: int) -> None:
+    n_out, k = w.shape
+    name = "emer_linear_tc_fwd" if _tc_rows_ok(n, k, n_out) else "emer_linear_fwd"
+    _lib.call(name, _ptr(x2), ldx, _ptr(w), _ptr(b), _ptr(y), ldy, n, k, n_out, act, _stream())
+
+
+def _layer_bwd_data(dz: Tensor, lddz: int, w: Tensor, dx: Tensor, lddx: int, n: int,
+                    relu_src: Optional[Tensor], ld_relu: int, relu_cols: int) -> None:
+    """dx[n, k] = dz[n, n_out] @ w, then dx[:, :relu_cols] *= (relu_src > 0) (the dZ of the layer below)."""
+    n_out, k = w.shape
+    if _tc_rows_ok(n, k, n_out):
+        _lib.call("emer_linear_tc_bwd_data", _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(w), _ptr(dx), lddx,
+                  _ptr(relu_src), ld_relu, relu_cols, n, k, n_out, 0, _stream())
+    else:
+        _lib.call("emer_linear_bwd_data", _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(w), _ptr(dx), lddx, n, k, n_out, 0,
+                  _stream())
+        if relu_src is not None:
+            dx[:, :relu_cols].mul_(relu_src[:, :relu_cols] > 0)
+
+
+def _layer_bwd_weight(x2: Tensor, ldx: int, dz: Tensor, lddz: int, w: Tensor, has_bias: bool, n: int):
+    n_out, k = w.shape
+    dw = torch.zeros_like(w)
+    db = torch.zeros(n_out, dtype=torch.float32, device=w.device) if has_bias else None
+    tc = (_tc_rows_ok(n, k, n_out) and LINEAR_WGRAD_IMPL == "tc" and n_out <= 128 and n_out % 4 == 0
+          and _aligned(x2, ldx) and _aligned(dz, lddz) and _pad4(k) <= ldx)
+    if tc:
+        _lib.call("emer_linear_tc_bwd_weight", _ptr(x2), ldx, _ptr(dz), lddz, _ptr(dw), _ptr(db), n, k, n_out,
+                  _stream())
+    else:
+        _lib.call("emer_linear_bwd_weight", _ptr(x2), ldx, _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(dw), _ptr(db), n, k,
+                  n_out, _stream())
+    return dw, db
+
+
+class _MLPChain(torch.autograd.Function):
+    """A whole head: Linear -> ReLU -> ... -> Linear [-> out_act], optionally with the chain input
+    concatenated in front of layer ``skip_layer`` (radiance_fields/mlp.py:38-46).  Hidden activations
+    are written once (they are needed by the backward pass), the skip concatenation is assembled in
+    place (the previous layer writes straight into the concat buffer), and in the backward pass every
+    data-gradient kernel applies the ReLU mask of the layer below in its epilogue, so no
+    activation-derivative pass ever runs on its own."""
+
     @staticmethod
-    def forward(ctx, x: Tensor, w: Tensor, b: Optional[Tensor], act: int):
+    def forward(ctx, x: Tensor, skip_layer: int, out_act: int, has_bias: bool, *params: Tensor):
         ctx.set_materialize_grads(False)
-        _need_cuda(x, w)
-        n_out, k = w.shape
+        ws = [_f32c(w) for w in (params[0::2] if has_bias else params)]
+        bs = [_f32c(b) for b in params[1::2]] if has_bias else [None] * len(ws)
+        _need_cuda(x, *ws)
+        k0 = ws[0].shape[1]
         lead = x.shape[:-1]
-        x2, ldx = _rows(x, k)
-        w = _f32c(w)
-        bb = None if b is None else _f32c(b)
+        x2, ldx = _rows(x, k0)
         n = x2.shape[0]
-        y = torch.empty((n, n_out), dtype=torch.float32, device=x.device)
-        use_tc = LINEAR_IMPL == "tc" and n >= TC_MIN_ROWS and k <= 256 and n_out <= 256
-        _lib.call("emer_linear_tc_fwd" if use_tc else "emer_linear_fwd", _ptr(x2), ldx, _ptr(w), _ptr(bb), _ptr(y),
-                  n_out, n, k, n_out, act, _stream())
-        ctx.save_for_backward(x2, w, y if act != ACT_NONE else None)
-        ctx.act, ctx.ldx, ctx.x_shape, ctx.has_bias, ctx.use_tc = act, ldx, x.shape, b is not None, use_tc
-        return y.view(*lead, n_out)
+        dev = x.device
+        L = len(ws)
+        inputs, lds, outs = [], [], []
+        cur, ld = x2, ldx
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            n_out, k = w.shape
+            if i == skip_layer and i > 0:
+                # cur is catbuf[:, :h] (written by layer i-1); the chain input goes behind it
+                h = ws[i - 1].shape[0]
+                catbuf = cur._base if cur._base is not None else cur
+                catbuf[:, h:h + k0].copy_(x2)
+                cur, ld = catbuf[:, :h + k0], catbuf.shape[1]
+            if cur.shape[1] != k:
+                raise ValueError(f"mlp layer {i}: input width {cur.shape[1]} != weight width {k}")
+            act = ACT_RELU if i < L - 1 else out_act
+            if i + 1 == skip_layer and i + 1 < L:
+                buf = torch.empty((n, _pad4(n_out + k0)), dtype=torch.float32, device=dev)
+                if buf.shape[1] > n_out + k0:
+                    buf[:, n_out + k0:].zero_()
+                y, ldy = buf[:, :n_out], buf.shape[1]
+            else:
+                y = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+                ldy = n_out
+            _layer_fwd(cur, ld, w, b, y, ldy, n, act)
+            inputs.append(cur)
+            lds.append(ld)
+            outs.append(y)
+            cur, ld = y, ldy
+        ctx.save_for_backward(*inputs, outs[-1], *ws)
+        ctx.meta = (skip_layer, out_act, has_bias, L, lds, k0, x.shape)
+        return outs[-1].view(*lead, -1)
 
     @staticmethod
     def backward(ctx, dy):
+        skip_layer, out_act, has_bias, L, lds, k0, x_shape = ctx.meta
+        n_grads = 4 + (2 * L if has_bias else L)
         if dy is None:
-            return None, None, None, None
-        x2, w, y = ctx.saved_tensors
-        n_out, k = w.shape
-        n = x2.shape[0]
-        dy2, lddy = _rows(dy, n_out)
-        dx = dw = db = None
-        st = _stream()
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty((n, k), dtype=torch.float32, device=dy.device)
-            _lib.call("emer_linear_tc_bwd_data" if ctx.use_tc else "emer_linear_bwd_data", _ptr(dy2), lddy, _ptr(y), n_out, ctx.act, _ptr(w), _ptr(dx), k, n, k,
-                      n_out, 0, st)
-            dx = dx.view(ctx.x_shape)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.zeros_like(w)
-            db = torch.zeros(n_out, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-            tc_w = ctx.use_tc and LINEAR_WGRAD_IMPL == "tc" and n_out <= 128
-            _lib.call("emer_linear_tc_bwd_weight" if tc_w else "emer_linear_bwd_weight", _ptr(x2), ctx.ldx, _ptr(dy2), lddy, _ptr(y), n_out, ctx.act,
-                      _ptr(dw), _ptr(db), n, k, n_out, st)
-        return dx, dw, db, None
+            return (None,) * n_grads
+        saved = ctx.saved_tensors
+        inputs, y_last, ws = saved[:L], saved[L], saved[L + 1:]
+        n = inputs[0].shape[0]
+        n_last = ws[-1].shape[0]
+        dz, lddz = _rows(dy, n_last)
+        if out_act == ACT_SIGMOID:
+            dz = dz * (y_last * (1.0 - y_last))
+            lddz = n_last
+        elif out_act == ACT_RELU:
+            dz = dz * (y_last > 0)
+            lddz = n_last
+        elif not dz.is_contiguous() and dz.shape[0] > 1 and lddz % 4 != 0:
+            dz, lddz = dz.contiguous(), n_last
+        need_x = ctx.needs_input_grad[0]
+        grads_w = [None] * L
+        grads_b = [None] * L
+        dx = None
+        dx_skip = None
+        for i in range(L - 1, -1, -1):
+            w = ws[i]
+            n_out, k = w.shape
+            inp, ld = inputs[i], lds[i]
+            w_idx = 4 + (2 * i if has_bias else i)
+            if ctx.needs_input_grad[w_idx] or (has_bias and ctx.needs_input_grad[w_idx + 1]):
+                grads_w[i], grads_b[i] = _layer_bwd_weight(inp, ld, dz, lddz, w, has_bias, n)
+            if i == 0 and not need_x:
+                break
+            d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dz.device)
+            if i > 0:
+                h = ws[i - 1].shape[0]          # first h columns of this layer's input are ReLU outputs
+                _layer_bwd_data(dz, lddz, w, d_inp, d_inp.shape[1], n, inp, ld, h)
+                if i == skip_layer:
+                    dx_skip = d_inp[:, h:h + k0]
+                dz, lddz = d_inp[:, :h], d_inp.shape[1]
+            else:
+                _layer_bwd_data(dz, lddz, w, d_inp, d_inp.shape[1], n, None, 0, 0)
+                dx = d_inp[:, :k]
+        if need_x:
+            if dx_skip is not None:
+                dx = dx + dx_skip
+            dx = dx.reshape(x_shape)
+        out = [dx if need_x else None, None, None, None]
+        for i in range(L):
+            out.append(grads_w[i])
+            if has_bias:
+                out.append(grads_b[i])
+        return tuple(out)
+
+
+def mlp_chain(x: Tensor, weights, biases=None, out_act: int = ACT_NONE, skip_layer: int = -1) -> Tensor:
+    """Evaluate a ReLU MLP head.  ``weights[i]``: [n_out_i, k_i] (nn.Linear layout); ``skip_layer``: the
+    layer in front of which [hidden, x] is concatenated (-1: none)."""
+    if x.shape[-1] != weights[0].shape[1]:
+        raise ValueError(f"mlp: input width {x.shape[-1]} != first layer width {weights[0].shape[1]}")
+    if biases is None:
+        return _MLPChain.apply(x, skip_layer, out_act, False, *weights)
+    flat = []
+    for w, b in zip(weights, biases):
+        flat += [w, b]
+    return _MLPChain.apply(x, skip_layer, out_act, True, *flat)
 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
     """act(x @ w.T + b) over the last dimension."""
     if x.shape[-1] != w.shape[1]:
         raise ValueError(f"linear: input width {x.shape[-1]} != weight width {w.shape[1]}")
-    return _Linear.apply(x, w, b, act)
+    return mlp_chain(x, [w], None if b is None else [b], act)
+
+
+def cat_pad4(parts, dim_check: bool = True) -> Tensor:
+    """torch.cat along the last dim into rows padded to a multiple of 4 floats (16-byte aligned rows
+    for the tensor-core loaders); returns the [..., total] view of the padded buffer."""
+    total = sum(p.shape[-1] for p in parts)
+    cat = torch.cat(parts, dim=-1)
+    pad = _pad4(total) - total
+    if pad == 0:
+        return cat
+    return torch.nn.functional.pad(cat, (0, pad))[..., :total]
 
 
 # ----------------------------------------------------------------------------- sampling

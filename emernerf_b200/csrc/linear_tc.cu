@@ -2,39 +2,45 @@
 //
 // The reference runs every head as fp32 nn.Linear, so a single-pass TF32 MMA
 // (10-bit mantissa) is not accurate enough for the 1e-4 parity bar.  Each fp32 operand is split
-// into tf32 hi + tf32 lo (x = hi + lo exactly to ~2^-21) and a product is accumulated in TMEM as
-//     A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          ("3xTF32", error ~1e-6 relative)
-// by three tcgen05.mma.kind::tf32 instructions per 8-wide k step.
+// into tf32 hi + tf32 lo (x = hi + lo to ~2^-21) and a product is accumulated in TMEM as
+//     A_hi*B_hi  +  (A_lo*B_hi + A_hi*B_lo)          ("3xTF32", error ~1e-6 relative)
+// by three tcgen05.mma.kind::tf32 per 8-wide k step, into two independent TMEM accumulators
+// (two dependency chains for the tensor pipe) that the epilogue adds.
 //
-// Shared-memory operand layout (both operands, no swizzle, "chunk-major"): the tile is cut into
-// panels of 4 consecutive k (16 bytes); inside a panel row r sits at r*16 bytes:
+// Shared-memory operand layout (both operands, SWIZZLE_NONE, K-major, "panel-major"): the tile is
+// cut into panels of 4 consecutive k (16 bytes); inside a panel row r sits at r*16 bytes:
 //     offset(r, k) = (k/4)*PANEL + r*16 + (k%4)*4
-// which is the canonical K-major SWIZZLE_NONE UMMA layout with 8x16B core matrices,
-// SBO = 128 B (next 8 rows) and LBO = PANEL (next 4 k).  A panel of the A tile is 128 rows =
-// 2048 B, padded to 2064 B so that the 8 threads that fill one row's 128 B hit 8 distinct
-// bank groups (conflict-free 16-byte stores).
+// = the canonical UMMA layout of 8x16B core matrices with SBO = 128 B (next 8 rows) and
+// LBO = PANEL (next 4 k).  PANEL is padded by 16 B so the 8 threads that fill one row's 128 B hit
+// 8 distinct bank groups.  (Probed on B200 with tools/tc_probe.cu: this layout and SWIZZLE_128B
+// give identical results and MMA rate; MN-major tf32 operands without swizzle return zeros, so the
+// weight-gradient kernel transposes while staging and stays K-major.)
 //
-// One CTA = 128 threads = 128 rows = 128 TMEM lanes.  Thread t owns row t in the loader, and lane
-// t of the accumulator in the epilogue (tcgen05.ld 32x32b: warp w reads lanes 32w..32w+31).
-// The A tile streams through a 2-stage ring of 32-wide k chunks (mbarrier, released by
-// tcgen05.commit); the B operand (the layer's weights, hi and lo) is resident for the CTA's life.
+// One CTA = 128 threads = 128 rows = 128 TMEM lanes (thread t owns row t in the epilogue:
+// tcgen05.ld 32x32b, warp w reads lanes 32w..32w+31).  Global -> shared goes through a ring of
+// cp.async (LDGSTS) stages of raw fp32 -- bytes in flight do not depend on occupancy (the first
+// version loaded through registers and sat on long-scoreboard stalls at 12 % active warps, see
+// profiles/) -- then each thread converts exactly the 16-byte pieces it copied (no barrier needed
+// between copy and convert), and one elected thread issues the MMAs.  Completion is tracked with
+// mbarriers armed by tcgen05.commit.
 //
-//   forward        Y  = act(X W^T + b)       A = X[128 x k],   B = W   [n_out x k]
-//   backward-data  dX = (dY * act'(Y)) W     A = dZ[128 x n_out], B = W^T [k x n_out]
+//   forward        Y  = act(X W^T + b)                  A = X[128 x k],      B = W   [n_out x k]
+//   backward-data  dX = dZ W   (* relu-mask epilogue)   A = dZ[128 x n_out], B = W^T [k x n_out]
+//   backward-wgt   dW^T = X^T dZ, accumulated in TMEM   A = X^T[k x rows],   B = dZ^T [n_out x rows]
 //
-// Roofline: these per-layer kernels are HBM-bound (read X, write Y: (k + n_out)*4 B per row); the
-// tensor pipe needs 3 * ceil(k/8) MMAs of 128 x n_pad per tile.
+// Roofline: HBM-bound per layer -- (k + n_out)*4 B per row forward.
 #include "common.cuh"
 
 namespace emer {
 namespace tc {
 
 constexpr int ROWS = 128;
-constexpr int CHUNK = 32;                    // k per ring stage
-constexpr int PANELS_PER_CHUNK = CHUNK / 4;  // 8
+constexpr int CHUNK = 32;                    // k per pipeline stage
 constexpr int A_PANEL = ROWS * 16 + 16;      // 2064 B (padded LBO)
-constexpr int A_STAGE = PANELS_PER_CHUNK * A_PANEL;   // one of hi / lo
-constexpr int STAGES = 2;
+constexpr int A_STAGE = (CHUNK / 4) * A_PANEL;   // one of hi / lo: 16512 B
+constexpr int A_STAGES = 2;                  // operand ring
+constexpr int RAW_STAGE = ROWS * CHUNK * 4;  // 16 KB of raw fp32 per chunk
+constexpr int RAW_STAGES = 4;                // cp.async ring depth
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -104,6 +110,34 @@ __device__ __forceinline__ void split(float x, float& hi, float& lo) {
     hi = to_tf32(x);
     lo = to_tf32(x - hi);
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// 16 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
     if (act == EMER_ACT_RELU) return v > 0.0f ? v : 0.0f;
@@ -125,6 +159,9 @@ struct Params {
     const float* bias;    // fwd only
     float* c;             // fwd: Y [n, ldc]      bwd: dX [n, ldc]
     int64_t ldc;
+    const float* relu_src;   // bwd: dX[:, :relu_cols] *= (relu_src > 0)  (layer input = a ReLU output)
+    int64_t ld_relu;
+    int relu_cols;
     int64_t n;            // rows
     int k, n_out;         // layer widths
     int kred;             // reduction width: fwd k, bwd n_out
@@ -133,46 +170,85 @@ struct Params {
     int n_pad;            // multiple of 16, <= 256
     int act;
     int accumulate;       // bwd: dX += result
-    int tmem_cols;        // power of two >= n_pad, >= 32
+    int tmem_cols;        // power of two >= 2*n_pad
+    int use_async;        // cp.async ring (16-byte aligned rows, no act' in the loader)
 };
 
 template <bool BWD>
 __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [B_hi | B_lo | A ring: STAGES x (hi, lo) | barriers]
+    // layout: [B_hi | B_lo | A ring: A_STAGES x (hi, lo) | raw ring | barriers]
     const int b_panel = p.n_pad * 16;
     const int b_bytes = (p.kred_pad / 4) * b_panel;
     uint8_t* b_hi = smem;
     uint8_t* b_lo = smem + b_bytes;
     uint8_t* a_ring = smem + 2 * b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + STAGES * 2 * A_STAGE);
-    uint64_t* empty_bar = bars;                 // [STAGES]
-    uint64_t* accum_bar = bars + STAGES;        // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES + 1);
+    uint8_t* raw = a_ring + A_STAGES * 2 * A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + (p.use_async ? RAW_STAGES * RAW_STAGE : 0));
+    uint64_t* empty_bar = bars;                  // [A_STAGES]
+    uint64_t* accum_bar = bars + A_STAGES;       // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + A_STAGES + 1);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        for (int s = 0; s < A_STAGES; ++s) mbar_init(&empty_bar[s], 1);
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     }
-    // ---- resident B operand: hi/lo panels of W (fwd: B[n][k] = W[n,k]; bwd: B[n=k_in][r=o] = W[o,k_in])
-    {
-        const int total = p.n_pad * p.kred_pad;
-        for (int e = tid; e < total; e += 128) {
-            const int r = e % p.kred_pad;      // reduction index
-            const int nn = e / p.kred_pad;     // B row (output column of the GEMM)
+    const int n_chunks = (p.kred_pad + CHUNK - 1) / CHUNK;
+    const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
+    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int total = my_tiles * n_chunks;
+
+    // cp.async producer: chunk g -> raw stage g % RAW_STAGES.  Thread t copies, for i in 0..7, the
+    // 16 bytes (row = i*16 + t/8, quad = t%8) into its own slot (i*128 + t): a row's 128 B are read
+    // by 8 consecutive threads (coalesced) and the slots of a warp are contiguous (conflict-free).
+    auto issue = [&](int g) {
+        const int tl = g / n_chunks, c = g - tl * n_chunks;
+        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * ROWS;
+        const int k0 = c * CHUNK;
+        uint8_t* dst = raw + (g % RAW_STAGES) * RAW_STAGE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 16 + (tid >> 3);
+            const int kk = k0 + (tid & 7) * 4;
+            const int64_t row = row0 + r;
+            const bool ok = (row < p.n) && (kk < p.kred);
+            const float* src = ok ? (p.a + row * p.lda + kk) : p.a;
+            cp_async16(dst + (i * 128 + tid) * 16, src, ok ? 16u : 0u);
+        }
+    };
+    if (p.use_async) {
+#pragma unroll
+        for (int g = 0; g < RAW_STAGES - 1; ++g) {
+            if (g < total) issue(g);
+            cp_async_commit();
+        }
+    }
+
+    // ---- resident B operand: hi/lo panels of W (fwd: B[n][r] = W[n, r]; bwd: B[n = k_in][r = o] = W[o, k_in])
+    if (!BWD) {
+        for (int e = tid; e < p.n_pad * p.kred_pad; e += 128) {
+            const int nn = e / p.kred_pad, r = e - nn * p.kred_pad;       // consecutive threads: consecutive r
             float v = 0.0f;
-            if (r < p.kred && nn < p.ncols) v = BWD ? __ldg(p.w + (int64_t)r * p.k + nn) : __ldg(p.w + (int64_t)nn * p.k + r);
+            if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)nn * p.k + r);
+            float hi, lo;
+            split(v, hi, lo);
+            const int off = (r >> 2) * b_panel + nn * 16 + (r & 3) * 4;
+            *reinterpret_cast<float*>(b_hi + off) = hi;
+            *reinterpret_cast<float*>(b_lo + off) = lo;
+        }
+    } else {
+        for (int e = tid; e < p.n_pad * p.kred_pad; e += 128) {
+            const int r = e / p.n_pad, nn = e - r * p.n_pad;              // consecutive threads: consecutive k_in
+            float v = 0.0f;
+            if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)r * p.k + nn);
             float hi, lo;
             split(v, hi, lo);
             const int off = (r >> 2) * b_panel + nn * 16 + (r & 3) * 4;
@@ -186,115 +262,119 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = make_idesc(128, p.n_pad);
-    const int n_chunks = (p.kred_pad + CHUNK - 1) / CHUNK;
-    const bool vec_a = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0) &&
-                       (!BWD || p.act == EMER_ACT_NONE || ((p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.yact) & 15) == 0)));
+    const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+    const bool vec_m = p.relu_src && (p.ld_relu % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.relu_src) & 15) == 0);
 
-    uint32_t stage_use[STAGES] = {0, 0};      // how many times each ring stage has been filled
-    uint32_t tiles_done = 0;
-    const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * ROWS;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int s = c & 1;
-            // the MMAs that last read this stage must have completed
-            if (stage_use[s] > 0) mbar_wait(&empty_bar[s], (stage_use[s] - 1) & 1);
-            uint8_t* a_hi = a_ring + (s * 2) * A_STAGE;
-            uint8_t* a_lo = a_hi + A_STAGE;
-            const int k0 = c * CHUNK;
-            // 128 rows x 8 float4: thread t -> (row = i*16 + t/8, quad = t%8): a row's 128 B are read by 8
-            // consecutive threads (coalesced) and land in 8 different panels (conflict-free, padded LBO)
+    for (int g = 0; g < total; ++g) {
+        const int tl = g / n_chunks, c = g - tl * n_chunks;
+        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * ROWS;
+        const int k0 = c * CHUNK;
+        const int s = g & 1;
+        uint8_t* a_hi = a_ring + (s * 2) * A_STAGE;
+        uint8_t* a_lo = a_hi + A_STAGE;
+        if (p.use_async) {
+            if (g + RAW_STAGES - 1 < total) issue(g + RAW_STAGES - 1);
+            cp_async_commit();
+            cp_async_wait<RAW_STAGES - 1>();          // this thread's pieces of chunk g have landed
+        }
+        // the MMAs that last read operand stage s (chunk g-2) must have retired
+        if (g >= A_STAGES) mbar_wait(&empty_bar[s], ((g >> 1) - 1) & 1);
+        const uint8_t* rs = raw + (g % RAW_STAGES) * RAW_STAGE;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = i * 16 + (tid >> 3);
-                const int q = tid & 7;
-                const int kk = k0 + q * 4;
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 16 + (tid >> 3);
+            const int q = tid & 7;
+            const int kk = k0 + q * 4;
+            float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (p.use_async) {
+                const float4 t = *reinterpret_cast<const float4*>(rs + (i * 128 + tid) * 16);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (kk + j >= p.kred) v[j] = 0.0f;
+            } else {
                 const int64_t row = row0 + r;
-                float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (row < p.n && kk < p.kred) {
-                    if (vec_a && kk + 3 < p.lda) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.a + row * p.lda + kk));
-                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                        if (BWD && p.act != EMER_ACT_NONE) {
-                            const float4 y = __ldg(reinterpret_cast<const float4*>(p.yact + row * p.ldy + kk));
-                            v[0] = act_bwd(v[0], y.x, p.act); v[1] = act_bwd(v[1], y.y, p.act);
-                            v[2] = act_bwd(v[2], y.z, p.act); v[3] = act_bwd(v[3], y.w, p.act);
-                        }
+                if (row < p.n) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (kk + j >= p.kred) v[j] = 0.0f;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (kk + j < p.kred) {
-                                float t = __ldg(p.a + row * p.lda + kk + j);
-                                if (BWD && p.act != EMER_ACT_NONE) t = act_bwd(t, __ldg(p.yact + row * p.ldy + kk + j), p.act);
-                                v[j] = t;
-                            }
+                    for (int j = 0; j < 4; ++j) {
+                        if (kk + j < p.kred) {
+                            float t = __ldg(p.a + row * p.lda + kk + j);
+                            if (BWD && p.act != EMER_ACT_NONE) t = act_bwd(t, __ldg(p.yact + row * p.ldy + kk + j), p.act);
+                            v[j] = t;
                         }
                     }
                 }
-                float4 h, l;
-                split(v[0], h.x, l.x); split(v[1], h.y, l.y); split(v[2], h.z, l.z); split(v[3], h.w, l.w);
-                *reinterpret_cast<float4*>(a_hi + q * A_PANEL + r * 16) = h;
-                *reinterpret_cast<float4*>(a_lo + q * A_PANEL + r * 16) = l;
             }
-            fence_async_proxy();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const int ksteps = min(CHUNK, p.kred_pad - k0) / 8;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint32_t a_off = (uint32_t)(ks * 2) * A_PANEL;
-                    const uint32_t b_off = (uint32_t)((k0 >> 2) + ks * 2) * b_panel;
-                    const uint64_t da_hi = make_desc(smem_u32(a_hi) + a_off, A_PANEL, 128);
-                    const uint64_t da_lo = make_desc(smem_u32(a_lo) + a_off, A_PANEL, 128);
-                    const uint64_t db_hi = make_desc(smem_u32(b_hi) + b_off, b_panel, 128);
-                    const uint64_t db_lo = make_desc(smem_u32(b_lo) + b_off, b_panel, 128);
-                    const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
-                    mma_tf32(tmem_base, da_lo, db_hi, idesc, first);
-                    mma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-                    mma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
-                }
-                tc_commit(&empty_bar[s]);                  // stage reusable once these MMAs retire
-                if (c == n_chunks - 1) tc_commit(accum_bar);   // ... and the accumulator is complete
-            }
-            stage_use[s]++;
+            float4 h, l;
+            split(v[0], h.x, l.x); split(v[1], h.y, l.y); split(v[2], h.z, l.z); split(v[3], h.w, l.w);
+            *reinterpret_cast<float4*>(a_hi + q * A_PANEL + r * 16) = h;
+            *reinterpret_cast<float4*>(a_lo + q * A_PANEL + r * 16) = l;
         }
+        fence_async_proxy();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const int ksteps = min(CHUNK, p.kred_pad - k0) / 8;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t a_off = (uint32_t)(ks * 2) * A_PANEL;
+                const uint32_t b_off = (uint32_t)((k0 >> 2) + ks * 2) * b_panel;
+                const uint64_t da_hi = make_desc(smem_u32(a_hi) + a_off, A_PANEL, 128);
+                const uint64_t da_lo = make_desc(smem_u32(a_lo) + a_off, A_PANEL, 128);
+                const uint64_t db_hi = make_desc(smem_u32(b_hi) + b_off, b_panel, 128);
+                const uint64_t db_lo = make_desc(smem_u32(b_lo) + b_off, b_panel, 128);
+                const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
+                mma_tf32(tmem_base, da_hi, db_hi, idesc, first);                       // chain 0
+                mma_tf32(tmem_base + (uint32_t)p.n_pad, da_lo, db_hi, idesc, first);   // chain 1
+                mma_tf32(tmem_base + (uint32_t)p.n_pad, da_hi, db_lo, idesc, 1u);
+            }
+            tc_commit(&empty_bar[s]);                        // operand stage reusable once these retire
+            if (c == n_chunks - 1) tc_commit(accum_bar);     // ... and the tile's accumulators are complete
+        }
+        if (c != n_chunks - 1) continue;
+
         // ---- epilogue: TMEM -> registers -> global.  thread t = row t = TMEM lane t
-        mbar_wait(accum_bar, tiles_done & 1);
-        tiles_done++;
+        mbar_wait(accum_bar, tl & 1);
         tc_fence_after();
         const int64_t row = row0 + tid;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
         for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-            uint32_t r[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(lane_addr + (uint32_t)c0)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < p.n) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(lane_addr + (uint32_t)c0, r0);
+            tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
+            tmem_ld_wait();
+            if (row < p.n && c0 < p.ncols) {
                 float* out = p.c + row * p.ldc + c0;
 #pragma unroll
                 for (int j0 = 0; j0 < 16; j0 += 4) {
+                    if (c0 + j0 >= p.ncols) break;
                     float o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int col = c0 + j0 + j;
-                        float v = __uint_as_float(r[j0 + j]);
+                        float v = __uint_as_float(r0[j0 + j]) + __uint_as_float(r1[j0 + j]);
                         if (!BWD) {
                             if (p.bias && col < p.ncols) v += __ldg(p.bias + col);
                             v = act_fwd(v, p.act);
                         }
                         o[j] = v;
                     }
-                    if (vec_c && c0 + j0 + 3 < p.ncols) {
+                    const bool full = c0 + j0 + 3 < p.ncols;
+                    if (BWD && p.relu_src && c0 + j0 < p.relu_cols) {
+                        const float* m = p.relu_src + row * p.ld_relu + c0 + j0;
+                        if (vec_m && full && c0 + j0 + 3 < p.relu_cols) {
+                            const float4 mm = __ldg(reinterpret_cast<const float4*>(m));
+                            if (!(mm.x > 0.0f)) o[0] = 0.0f;
+                            if (!(mm.y > 0.0f)) o[1] = 0.0f;
+                            if (!(mm.z > 0.0f)) o[2] = 0.0f;
+                            if (!(mm.w > 0.0f)) o[3] = 0.0f;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (c0 + j0 + j < p.ncols && c0 + j0 + j < p.relu_cols && !(__ldg(m + j) > 0.0f)) o[j] = 0.0f;
+                        }
+                    }
+                    if (vec_c && full) {
                         float4* dst = reinterpret_cast<float4*>(out + j0);
                         if (BWD && p.accumulate) {
                             const float4 old = *dst;
@@ -313,21 +393,16 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
                 }
             }
         }
-        tc_fence_before();      // TMEM reads done before the next tile's first MMA overwrites the accumulator
+        tc_fence_before();      // TMEM reads done before the next tile's first MMA overwrites the accumulators
         __syncthreads();
     }
+    if (p.use_async) cp_async_wait<0>();
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                     : "memory");
-    }
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-static size_t smem_bytes(const Params& p) {
-    return (size_t)2 * (p.kred_pad / 4) * p.n_pad * 16 + (size_t)STAGES * 2 * A_STAGE + (STAGES + 1) * 8 + 16;
-}
 
 template <bool BWD>
 static int launch(Params& p, cudaStream_t st, const char* what) {
@@ -337,8 +412,11 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
     p.n_pad = round_up(p.ncols, 16);
     EMER_REQUIRE(p.n_pad <= 256, "%s: output width %d exceeds one MMA (256)", what, p.ncols);
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.n_pad) p.tmem_cols *= 2;
-    const size_t smem = smem_bytes(p);
+    while (p.tmem_cols < 2 * p.n_pad) p.tmem_cols *= 2;
+    const size_t base = (size_t)2 * (p.kred_pad / 4) * p.n_pad * 16 + (size_t)A_STAGES * 2 * A_STAGE + (A_STAGES + 1) * 8 + 16;
+    p.use_async = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0) && !(BWD && p.act != EMER_ACT_NONE) &&
+                  (base + (size_t)RAW_STAGES * RAW_STAGE <= 227 * 1024);
+    const size_t smem = base + (p.use_async ? (size_t)RAW_STAGES * RAW_STAGE : 0);
     EMER_REQUIRE(smem <= 227 * 1024, "%s: layer %dx%d needs %zu B of shared memory", what, p.k, p.n_out, smem);
     static size_t configured[2] = {0, 0};
     if (smem > configured[BWD]) {
@@ -350,7 +428,7 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
         configured[BWD] = smem;
     }
     const int64_t n_tiles = ceil_div(p.n, ROWS);
-    const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
     int64_t grid = 148 * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
     tc_linear_kernel<BWD><<<(unsigned)grid, 128, smem, st>>>(p);
@@ -358,6 +436,206 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
 }
 
 }  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient:  dW^T[k, n_out] += X^T dZ,  db += sum_rows dZ.
+//
+// The reduction runs over the ROWS.  tf32 operands must stay K-major (see the probe note above), so
+// the staging step transposes: a tile is 64 rows; panel rq holds rows 4rq..4rq+3 as the 16-byte
+// "k" group and the FEATURE is the operand row:   offset(f, r) = (r/4)*PANEL + f*16 + (r%4)*4.
+// A = X^T (M = one 128-feature block of k), B = dZ^T (N = n_out), 8 tf32 k-steps per tile.
+// Raw fp32 rows arrive through cp.async; each thread then gathers 4 rows x 1 feature from the raw
+// tile (conflict-free: consecutive threads, consecutive features) and writes one 16-byte group.
+// Every persistent CTA keeps dW^T in TMEM across all of its tiles (hi*hi chain and cross-term
+// chain per 128-feature block) and flushes once with atomics.
+namespace tcw {
+
+using namespace emer::tc;
+
+constexpr int WROWS = 64;                     // rows per tile = 16 row-quads = 8 tf32 k-steps
+constexpr int RQ = WROWS / 4;
+
+struct WParams {
+    const float* x;
+    int64_t ldx;
+    const float* dz;     // dZ (activation derivative already applied)
+    int64_t lddz;
+    float* dw;           // [n_out, k]
+    float* db;           // [n_out] or null
+    int64_t n;
+    int k, n_out;
+    int k_pad4;          // k rounded to 4  (raw row width)
+    int n_pad;           // n_out rounded to 16
+    int m_blocks;        // ceil(k / 128)
+    int raw_stages;      // 1 or 2
+    int tmem_cols;
+};
+
+__global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int a_panel = 128 * 16 + 16;                     // 2064
+    const int b_panel = p.n_pad * 16 + 16;
+    const int a_bytes = p.m_blocks * RQ * a_panel;         // one of hi / lo
+    const int b_bytes = RQ * b_panel;
+    const int rawx_bytes = WROWS * p.k_pad4 * 4;
+    const int rawz_bytes = WROWS * p.n_pad * 4;
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + a_bytes;
+    uint8_t* b_hi = a_lo + a_bytes;
+    uint8_t* b_lo = b_hi + b_bytes;
+    uint8_t* raw = b_lo + b_bytes;                          // raw_stages x (X rows | dZ rows)
+    const int raw_stage = rawx_bytes + rawz_bytes;
+    uint64_t* done_bar = reinterpret_cast<uint64_t*>(raw + p.raw_stages * raw_stage);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
+    // operand buffers start as zeros: padding features / columns never hold NaN bit patterns
+    for (int i = tid * 16; i < 2 * a_bytes + 2 * b_bytes; i += 128 * 16)
+        *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int64_t n_tiles = (p.n + WROWS - 1) / WROWS;
+    const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int xq = p.k_pad4 / 4, zq = p.n_pad / 4;
+
+    auto issue = [&](int t) {
+        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * WROWS;
+        uint8_t* dx = raw + (t % p.raw_stages) * raw_stage;
+        uint8_t* dzs = dx + rawx_bytes;
+        for (int e = tid; e < WROWS * xq; e += 128) {
+            const int r = e / xq, q = e - r * xq;
+            const int64_t row = row0 + r;
+            const bool ok = (row < p.n) && (q * 4 < p.k);
+            cp_async16(dx + e * 16, ok ? (p.x + row * p.ldx + q * 4) : p.x, ok ? 16u : 0u);
+        }
+        for (int e = tid; e < WROWS * zq; e += 128) {
+            const int r = e / zq, q = e - r * zq;
+            const int64_t row = row0 + r;
+            const bool ok = (row < p.n) && (q * 4 < p.n_out);
+            cp_async16(dzs + e * 16, ok ? (p.dz + row * p.lddz + q * 4) : p.dz, ok ? 16u : 0u);
+        }
+    };
+    for (int t = 0; t < p.raw_stages; ++t) {
+        if (t < my_tiles) issue(t);
+        cp_async_commit();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = make_idesc(128, p.n_pad);
+    float bsum = 0.0f;        // thread t < n_out owns db[t]
+
+    for (int t = 0; t < my_tiles; ++t) {
+        // raw tile t landed?  (each thread waits for its own pieces, the barrier below publishes all)
+        if (p.raw_stages == 2) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        // the previous tile's MMAs must have finished reading the operand buffers
+        if (t > 0) mbar_wait(done_bar, (t - 1) & 1);
+        const float* rx = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage);
+        const float* rz = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage + rawx_bytes);
+        // ---- A = X^T: item (rq, f): rows 4rq..4rq+3 of feature f -> one 16-byte k group
+        for (int e = tid; e < RQ * p.k_pad4; e += 128) {
+            const int rq = e / p.k_pad4, f = e - rq * p.k_pad4;
+            float4 h, l;
+            if (f < p.k) {
+                const float* src = rx + (rq * 4) * p.k_pad4 + f;
+                split(src[0], h.x, l.x);
+                split(src[p.k_pad4], h.y, l.y);
+                split(src[2 * p.k_pad4], h.z, l.z);
+                split(src[3 * p.k_pad4], h.w, l.w);
+            } else {
+                h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const int off = ((f >> 7) * RQ + rq) * a_panel + (f & 127) * 16;
+            *reinterpret_cast<float4*>(a_hi + off) = h;
+            *reinterpret_cast<float4*>(a_lo + off) = l;
+        }
+        // ---- B = dZ^T
+        for (int e = tid; e < RQ * p.n_pad; e += 128) {
+            const int rq = e / p.n_pad, o = e - rq * p.n_pad;
+            float4 h, l;
+            if (o < p.n_out) {
+                const float* src = rz + (rq * 4) * p.n_pad + o;
+                split(src[0], h.x, l.x);
+                split(src[p.n_pad], h.y, l.y);
+                split(src[2 * p.n_pad], h.z, l.z);
+                split(src[3 * p.n_pad], h.w, l.w);
+            } else {
+                h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            *reinterpret_cast<float4*>(b_hi + rq * b_panel + o * 16) = h;
+            *reinterpret_cast<float4*>(b_lo + rq * b_panel + o * 16) = l;
+        }
+        if (p.db && tid < p.n_out) {
+#pragma unroll 8
+            for (int r = 0; r < WROWS; ++r) bsum += rz[r * p.n_pad + tid];
+        }
+        fence_async_proxy();
+        tc_fence_before();
+        __syncthreads();                    // operands complete; raw stage t free again
+        if (t + p.raw_stages < my_tiles) issue(t + p.raw_stages);
+        cp_async_commit();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < WROWS / 8; ++ks) {
+                const uint32_t boff = (uint32_t)(ks * 2) * b_panel;
+                const uint64_t db_hi = make_desc(smem_u32(b_hi) + boff, b_panel, 128);
+                const uint64_t db_lo = make_desc(smem_u32(b_lo) + boff, b_panel, 128);
+                const uint32_t acc = (t == 0 && ks == 0) ? 0u : 1u;
+                for (int mb = 0; mb < p.m_blocks; ++mb) {
+                    const uint32_t aoff = (uint32_t)(mb * RQ + ks * 2) * a_panel;
+                    const uint64_t da_hi = make_desc(smem_u32(a_hi) + aoff, a_panel, 128);
+                    const uint64_t da_lo = make_desc(smem_u32(a_lo) + aoff, a_panel, 128);
+                    const uint32_t d0 = tmem_base + (uint32_t)(mb * 2 * p.n_pad);
+                    mma_tf32(d0, da_hi, db_hi, idesc, acc);                           // chain 0
+                    mma_tf32(d0 + (uint32_t)p.n_pad, da_lo, db_hi, idesc, acc);       // chain 1
+                    mma_tf32(d0 + (uint32_t)p.n_pad, da_hi, db_lo, idesc, 1u);
+                }
+            }
+            tc_commit(done_bar);
+        }
+    }
+    if (my_tiles > 0) {
+        mbar_wait(done_bar, (my_tiles - 1) & 1);
+        tc_fence_after();
+        // flush: lane f of block mb holds dW^T[mb*128 + f, :]
+        for (int mb = 0; mb < p.m_blocks; ++mb) {
+            const int f = mb * 128 + tid;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * 2 * p.n_pad);
+            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(lane_addr + (uint32_t)c0, r0);
+                tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
+                tmem_ld_wait();
+                if (f < p.k) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int o = c0 + j;
+                        if (o < p.n_out)
+                            atomicAdd(p.dw + (int64_t)o * p.k + f, __uint_as_float(r0[j]) + __uint_as_float(r1[j]));
+                    }
+                }
+            }
+        }
+        if (p.db && tid < p.n_out) atomicAdd(p.db + tid, bsum);
+    }
+    cp_async_wait<0>();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace tcw
 }  // namespace emer
 
 using namespace emer;
@@ -374,246 +652,44 @@ extern "C" int emer_linear_tc_fwd(const float* x, int64_t ldx, const float* w, c
 }
 
 extern "C" int emer_linear_tc_bwd_data(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act,
-                                       const float* w, float* dx, int64_t lddx, int64_t n, int k, int n_out,
-                                       int accumulate, void* stream) {
+                                       const float* w, float* dx, int64_t lddx, const float* relu_src,
+                                       int64_t ld_relu, int relu_cols, int64_t n, int k, int n_out, int accumulate,
+                                       void* stream) {
     if (n == 0) return 0;
     EMER_REQUIRE(dy && w && dx, "emer_linear_tc_bwd_data: NULL pointer");
     EMER_REQUIRE(act == EMER_ACT_NONE || y, "emer_linear_tc_bwd_data: activation needs the stored output");
     tc::Params p{};
     p.a = dy; p.lda = lddy; p.yact = y; p.ldy = ldy; p.w = w; p.bias = nullptr; p.c = dx; p.ldc = lddx;
+    p.relu_src = relu_src; p.ld_relu = ld_relu; p.relu_cols = relu_src ? relu_cols : 0;
     p.n = n; p.k = k; p.n_out = n_out; p.act = act; p.accumulate = accumulate;
     return tc::launch<true>(p, (cudaStream_t)stream, "emer_linear_tc_bwd_data");
 }
 
-// ------------------------------------------------------------------------------------------------
-// Weight gradient on the tensor cores:  dW^T[k, n_out] += X^T dZ,  db += sum_rows dZ.
-//
-// The reduction runs over the ROWS, so both operands are "MN-major": the chunk-major tile layout
-// above (offset(r, f) = (f/4)*PANEL + r*16 + (f%4)*4) is also the canonical MN-major SWIZZLE_NONE
-// UMMA layout with SBO = PANEL (next 4 features) and 8-row core matrices 128 B apart along the
-// reduction (one 8-row core matrix per tf32 k-step).  A = X^T (M = a 128-feature block of k),
-// B = dZ^T (N = n_out).  Each persistent CTA keeps dW^T in TMEM (one 128-lane block per 128
-// input features) across all of its 64-row tiles and flushes once with atomics.
-namespace emer {
-namespace tcw {
-
-using namespace emer::tc;
-
-constexpr int WROWS = 64;                     // rows per tile (8 tf32 k-steps)
-constexpr int W_PANEL = WROWS * 16 + 16;      // 1040 B
-
-struct WParams {
-    const float* x;
-    int64_t ldx;
-    const float* dy;
-    int64_t lddy;
-    const float* y;
-    int64_t ldy;
-    float* dw;       // [n_out, k]
-    float* db;       // [n_out] or null
-    int64_t n;
-    int k, n_out;
-    int k_pad4;      // k rounded to 4 (panels of the X tile)
-    int n_pad;       // n_out rounded to 16
-    int m_blocks;    // ceil(k / 128)
-    int x_panels_alloc;   // panels reserved for X (>= 32 * m_blocks so an M=128 operand never leaves smem)
-    int act;
-    int tmem_cols;
-};
-
-__global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int x_bytes = p.x_panels_alloc * W_PANEL;
-    const int z_panels = p.n_pad / 4;
-    const int z_bytes = z_panels * W_PANEL;
-    uint8_t* x_hi = smem;
-    uint8_t* x_lo = x_hi + x_bytes;
-    uint8_t* z_hi = x_lo + x_bytes;
-    uint8_t* z_lo = z_hi + z_bytes;
-    uint64_t* done_bar = reinterpret_cast<uint64_t*>(z_lo + z_bytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(done_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // zero the operand buffers once: padding panels / rows must never hold NaN bit patterns
-    for (int i = tid * 16; i < 2 * x_bytes + 2 * z_bytes; i += 128 * 16)
-        *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    // a=b=tf32, c=f32, A and B MN-major (bits 15, 16)
-    const uint32_t idesc = make_idesc(128, p.n_pad) | (1u << 15) | (1u << 16);
-
-    const int64_t n_tiles = (p.n + WROWS - 1) / WROWS;
-    uint32_t tiles_done = 0;
-    float bsum = 0.0f;        // thread t < n_out owns db[t]
-    const int x_quads = p.k_pad4 / 4;
-    const bool vec_x = (p.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
-    const bool vec_z = (p.lddy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dy) & 15) == 0) &&
-                       (p.act == EMER_ACT_NONE || ((p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0)));
-
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = tile * WROWS;
-        // the previous tile's MMAs must have finished reading the operand buffers
-        if (tiles_done > 0) mbar_wait(done_bar, (tiles_done - 1) & 1);
-        // ---- X tile: 64 rows x x_quads float4
-        for (int e = tid; e < WROWS * x_quads; e += 128) {
-            const int r = e / x_quads, q = e % x_quads;
-            const int64_t row = row0 + r;
-            const int kk = q * 4;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (row < p.n) {
-                if (vec_x && kk + 3 < p.ldx) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.x + row * p.ldx + kk));
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (kk + j >= p.k) v[j] = 0.f;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (kk + j < p.k) v[j] = __ldg(p.x + row * p.ldx + kk + j);
-                }
-            }
-            float4 h, l;
-            split(v[0], h.x, l.x); split(v[1], h.y, l.y); split(v[2], h.z, l.z); split(v[3], h.w, l.w);
-            *reinterpret_cast<float4*>(x_hi + q * W_PANEL + r * 16) = h;
-            *reinterpret_cast<float4*>(x_lo + q * W_PANEL + r * 16) = l;
-        }
-        // ---- dZ tile: 64 rows x z_panels float4, dZ = dY * act'(Y)
-        for (int e = tid; e < WROWS * z_panels; e += 128) {
-            const int r = e / z_panels, q = e % z_panels;
-            const int64_t row = row0 + r;
-            const int oo = q * 4;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (row < p.n && oo < p.n_out) {
-                if (vec_z && oo + 3 < p.lddy) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(p.dy + row * p.lddy + oo));
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                    if (p.act != EMER_ACT_NONE) {
-                        const float4 yy = __ldg(reinterpret_cast<const float4*>(p.y + row * p.ldy + oo));
-                        v[0] = act_bwd(v[0], yy.x, p.act); v[1] = act_bwd(v[1], yy.y, p.act);
-                        v[2] = act_bwd(v[2], yy.z, p.act); v[3] = act_bwd(v[3], yy.w, p.act);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (oo + j >= p.n_out) v[j] = 0.f;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (oo + j < p.n_out) {
-                            float t = __ldg(p.dy + row * p.lddy + oo + j);
-                            if (p.act != EMER_ACT_NONE) t = act_bwd(t, __ldg(p.y + row * p.ldy + oo + j), p.act);
-                            v[j] = t;
-                        }
-                    }
-                }
-            }
-            float4 h, l;
-            split(v[0], h.x, l.x); split(v[1], h.y, l.y); split(v[2], h.z, l.z); split(v[3], h.w, l.w);
-            *reinterpret_cast<float4*>(z_hi + q * W_PANEL + r * 16) = h;
-            *reinterpret_cast<float4*>(z_lo + q * W_PANEL + r * 16) = l;
-        }
-        fence_async_proxy();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            for (int mb = 0; mb < p.m_blocks; ++mb) {
-                const uint32_t d_addr = tmem_base + (uint32_t)(mb * p.n_pad);
-                const uint32_t xa = (uint32_t)(mb * 32) * W_PANEL;       // 128 features = 32 panels
-                for (int ks = 0; ks < WROWS / 8; ++ks) {
-                    const uint32_t roff = (uint32_t)ks * 128;            // next 8 rows
-                    const uint64_t da_hi = make_desc(smem_u32(x_hi) + xa + roff, 128, W_PANEL);
-                    const uint64_t da_lo = make_desc(smem_u32(x_lo) + xa + roff, 128, W_PANEL);
-                    const uint64_t db_hi = make_desc(smem_u32(z_hi) + roff, 128, W_PANEL);
-                    const uint64_t db_lo = make_desc(smem_u32(z_lo) + roff, 128, W_PANEL);
-                    const uint32_t acc = (tiles_done == 0 && ks == 0) ? 0u : 1u;
-                    mma_tf32(d_addr, da_lo, db_hi, idesc, acc);
-                    mma_tf32(d_addr, da_hi, db_lo, idesc, 1u);
-                    mma_tf32(d_addr, da_hi, db_hi, idesc, 1u);
-                }
-            }
-            tc_commit(done_bar);
-        }
-        // bias gradient from the staged dZ tile (hi + lo = the fp32 value to ~2^-21)
-        if (p.db && tid < p.n_out) {
-            const uint8_t* zh = z_hi + (tid >> 2) * W_PANEL + (tid & 3) * 4;
-            const uint8_t* zl = z_lo + (tid >> 2) * W_PANEL + (tid & 3) * 4;
-#pragma unroll 8
-            for (int r = 0; r < WROWS; ++r)
-                bsum += *reinterpret_cast<const float*>(zh + r * 16) + *reinterpret_cast<const float*>(zl + r * 16);
-        }
-        tiles_done++;
-    }
-    if (tiles_done > 0) {
-        mbar_wait(done_bar, (tiles_done - 1) & 1);
-        tc_fence_after();
-        // flush: lane f of block mb holds dW^T[mb*128 + f, :]
-        for (int mb = 0; mb < p.m_blocks; ++mb) {
-            const int f = mb * 128 + tid;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * p.n_pad);
-            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-                uint32_t r[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(lane_addr + (uint32_t)c0)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (f < p.k) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int o = c0 + j;
-                        if (o < p.n_out) atomicAdd(p.dw + (int64_t)o * p.k + f, __uint_as_float(r[j]));
-                    }
-                }
-            }
-        }
-        if (p.db && tid < p.n_out) atomicAdd(p.db + tid, bsum);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                     : "memory");
-    }
-}
-
-}  // namespace tcw
-}  // namespace emer
-
-extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const float* dy, int64_t lddy, const float* y,
-                                         int64_t ldy, int act, float* dw, float* db, int64_t n, int k, int n_out,
-                                         void* stream) {
+extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
+                                         float* db, int64_t n, int k, int n_out, void* stream) {
     using namespace emer::tcw;
     if (n == 0) return 0;
-    EMER_REQUIRE(x && dy && dw, "emer_linear_tc_bwd_weight: NULL pointer");
-    EMER_REQUIRE(act == EMER_ACT_NONE || y, "emer_linear_tc_bwd_weight: activation needs the stored output");
+    EMER_REQUIRE(x && dz && dw, "emer_linear_tc_bwd_weight: NULL pointer");
     EMER_REQUIRE(n_out <= 128 && k <= 256, "emer_linear_tc_bwd_weight: widths k=%d n_out=%d out of range", k, n_out);
+    EMER_REQUIRE(ldx % 4 == 0 && lddz % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dz & 15) == 0,
+                 "emer_linear_tc_bwd_weight: rows must be 16-byte aligned (ldx=%lld lddz=%lld)", (long long)ldx,
+                 (long long)lddz);
     WParams p{};
-    p.x = x; p.ldx = ldx; p.dy = dy; p.lddy = lddy; p.y = y; p.ldy = ldy; p.dw = dw; p.db = db;
-    p.n = n; p.k = k; p.n_out = n_out; p.act = act;
+    p.x = x; p.ldx = ldx; p.dz = dz; p.lddz = lddz; p.dw = dw; p.db = db;
+    p.n = n; p.k = k; p.n_out = n_out;
     p.k_pad4 = (k + 3) / 4 * 4;
+    EMER_REQUIRE(p.k_pad4 <= ldx, "emer_linear_tc_bwd_weight: row stride %lld shorter than padded width %d", (long long)ldx,
+                 p.k_pad4);
     p.n_pad = (n_out + 15) / 16 * 16;
+    EMER_REQUIRE((n_out + 3) / 4 * 4 <= lddz, "emer_linear_tc_bwd_weight: dZ rows too short");
     p.m_blocks = (k + 127) / 128;
-    p.x_panels_alloc = 32 * p.m_blocks;
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.m_blocks * p.n_pad) p.tmem_cols *= 2;
-    const size_t smem = (size_t)2 * p.x_panels_alloc * W_PANEL + (size_t)2 * (p.n_pad / 4) * W_PANEL + 8 + 16;
+    while (p.tmem_cols < p.m_blocks * 2 * p.n_pad) p.tmem_cols *= 2;
+    EMER_REQUIRE(p.tmem_cols <= 512, "emer_linear_tc_bwd_weight: accumulator does not fit TMEM");
+    const size_t ops = (size_t)2 * p.m_blocks * RQ * (128 * 16 + 16) + (size_t)2 * RQ * (p.n_pad * 16 + 16);
+    const size_t raw_stage = (size_t)WROWS * (p.k_pad4 + p.n_pad) * 4;
+    p.raw_stages = (ops + 2 * raw_stage + 64 <= 227 * 1024) ? 2 : 1;
+    const size_t smem = ops + p.raw_stages * raw_stage + 8 + 16;
     EMER_REQUIRE(smem <= 227 * 1024, "emer_linear_tc_bwd_weight: %zu B of shared memory", smem);
     static size_t configured = 0;
     if (smem > configured) {

@@ -34,13 +34,13 @@ class MLP(nn.Module):
         self.layers = nn.ModuleList([nn.Linear(a, b) for a, b in widths])
 
     def forward(self, x: Tensor, out_act: int = _ops.ACT_NONE) -> Tensor:
-        skip_in = x
-        last = len(self.layers) - 1
-        for i, layer in enumerate(self.layers):
-            if i in self.skip_connections:
-                x = torch.cat([x, skip_in], -1)
-            x = _ops.linear(x, layer.weight, layer.bias, _ops.ACT_RELU if i < last else out_act)
-        return x
+        skips = [i for i in self.skip_connections if 0 < i < len(self.layers)]
+        if 0 in self.skip_connections:
+            x = torch.cat([x, x], -1)             # mlp.py:42-43 with i == 0 (never used by the model)
+        if len(skips) > 1:
+            raise NotImplementedError("more than one skip connection")
+        return _ops.mlp_chain(x, [l.weight for l in self.layers], [l.bias for l in self.layers], out_act,
+                              skips[0] if skips else -1)
 
 
 def run_sequential(seq: nn.Sequential, x: Tensor, out_act: int = _ops.ACT_NONE) -> Tensor:
@@ -50,6 +50,4 @@ def run_sequential(seq: nn.Sequential, x: Tensor, out_act: int = _ops.ACT_NONE) 
     linears = [m for m in seq if isinstance(m, nn.Linear)]
     if any(isinstance(m, nn.Sigmoid) for m in seq):
         out_act = _ops.ACT_SIGMOID
-    for i, lin in enumerate(linears):
-        x = _ops.linear(x, lin.weight, lin.bias, _ops.ACT_RELU if i < len(linears) - 1 else out_act)
-    return x
+    return _ops.mlp_chain(x, [l.weight for l in linears], [l.bias for l in linears], out_act)

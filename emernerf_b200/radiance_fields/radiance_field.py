@@ -362,11 +362,10 @@ class RadianceField(nn.Module):
         emb = self._appearance(unit, data_dict)
         if emb is not None:
             h = torch.cat([h, emb], dim=-1)
-        results = {"rgb": self.rgb_head(torch.cat([h, geo_feats], dim=-1), out_act=_ops.ACT_SIGMOID)}
+        results = {"rgb": self.rgb_head(_ops.cat_pad4([h, geo_feats]), out_act=_ops.ACT_SIGMOID)}
         if self.dynamic_xyz_encoder is not None:
             assert dynamic_geo_feats is not None, "Dynamic geometry features are not provided."
-            results["dynamic_rgb"] = self.rgb_head(torch.cat([h, dynamic_geo_feats], dim=-1),
-                                                   out_act=_ops.ACT_SIGMOID)
+            results["dynamic_rgb"] = self.rgb_head(_ops.cat_pad4([h, dynamic_geo_feats]), out_act=_ops.ACT_SIGMOID)
         return results
 
     def query_sky(self, directions: Tensor, data_dict: Dict[str, Tensor] = None) -> Dict[str, Tensor]:

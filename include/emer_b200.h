@@ -100,13 +100,16 @@ int emer_linear_bwd_weight(const float* x, int64_t ldx, const float* dy, int64_t
 int emer_linear_tc_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y,
                        int64_t ldy, int64_t n, int k, int n_out, int act, void* stream);
 int emer_linear_tc_bwd_data(const float* dy, int64_t lddy, const float* y, int64_t ldy, int act,
-                            const float* w, float* dx, int64_t lddx, int64_t n, int k, int n_out,
+                            const float* w, float* dx, int64_t lddx, const float* relu_src,
+                            int64_t ld_relu, int relu_cols, int64_t n, int k, int n_out,
                             int accumulate, void* stream);
-/* dW[n_out, k] += dZ^T X, db += column sums of dZ; dW^T accumulates in TMEM across the CTA's row
- * tiles (MN-major operands), flushed once with atomics.  k <= 256, n_out <= 128. */
-int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const float* dy, int64_t lddy,
-                              const float* y, int64_t ldy, int act, float* dw, float* db,
-                              int64_t n, int k, int n_out, void* stream);
+/* relu_src (may be NULL): the layer's input when that input is itself a ReLU output; the epilogue
+ * then writes dX[:, :relu_cols] * (relu_src > 0), i.e. the dZ of the layer below (fused mask). */
+/* dW[n_out, k] += dZ^T X, db += column sums of dZ (dZ = dY * act'(Y) supplied by the caller).
+ * dW^T accumulates in TMEM across each CTA's row tiles, flushed once with atomics.
+ * Needs 16-byte aligned rows (ldx, lddz multiples of 4); k <= 256, n_out <= 128. */
+int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
+                              float* db, int64_t n, int k, int n_out, void* stream);
 
 /* ---- inverse-CDF resampling (replaces nerfacc.pdf.importance_sampling + _transform_stot,
  *      third_party/nerfacc_prop_net.py:153-160,172-175,299-339) ---------------------------- */
