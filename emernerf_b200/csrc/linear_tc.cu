@@ -41,6 +41,7 @@ constexpr int A_STAGE = (CHUNK / 4) * A_PANEL;   // one of hi / lo: 16512 B
 constexpr int A_STAGES = 2;                  // operand ring
 constexpr int RAW_STAGE = ROWS * CHUNK * 4;  // 16 KB of raw fp32 per chunk
 constexpr int RAW_STAGES = 4;                // cp.async ring depth
+constexpr int NT = 256;                      // threads per CTA: 8 warps convert, warps w and w+4 share a TMEM lane quadrant
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -106,9 +107,12 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// x = hi + lo with hi, lo representable in tf32 (low 13 mantissa bits clear).  Truncation instead of
+// cvt.rna keeps the split on the full-rate integer/FP pipes (cvt is a quarter-rate conversion);
+// |x - hi - lo| <= 2^-20 |x|.
 __device__ __forceinline__ void split(float x, float& hi, float& lo) {
-    hi = to_tf32(x);
-    lo = to_tf32(x - hi);
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
@@ -175,7 +179,7 @@ struct Params {
 };
 
 template <bool BWD>
-__global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
+__global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [B_hi | B_lo | A ring: A_STAGES x (hi, lo) | raw ring | barriers]
     const int b_panel = p.n_pad * 16;
@@ -206,22 +210,22 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int total = my_tiles * n_chunks;
 
-    // cp.async producer: chunk g -> raw stage g % RAW_STAGES.  Thread t copies, for i in 0..7, the
-    // 16 bytes (row = i*16 + t/8, quad = t%8) into its own slot (i*128 + t): a row's 128 B are read
+    // cp.async producer: chunk g -> raw stage g % RAW_STAGES.  Thread t copies, for i in 0..3, the
+    // 16 bytes (row = i*32 + t/8, quad = t%8) into its own slot (i*NT + t): a row's 128 B are read
     // by 8 consecutive threads (coalesced) and the slots of a warp are contiguous (conflict-free).
+    constexpr int PIECES = ROWS * (CHUNK / 4) / NT;     // 4
+    const int my_r = tid >> 3, my_q = tid & 7;
     auto issue = [&](int g) {
         const int tl = g / n_chunks, c = g - tl * n_chunks;
         const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * ROWS;
-        const int k0 = c * CHUNK;
-        uint8_t* dst = raw + (g % RAW_STAGES) * RAW_STAGE;
+        const int kk = c * CHUNK + my_q * 4;
+        const bool kok = kk < p.kred;
+        const float* base = p.a + (row0 + my_r) * p.lda + kk;
+        uint8_t* dst = raw + (g % RAW_STAGES) * RAW_STAGE + tid * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = i * 16 + (tid >> 3);
-            const int kk = k0 + (tid & 7) * 4;
-            const int64_t row = row0 + r;
-            const bool ok = (row < p.n) && (kk < p.kred);
-            const float* src = ok ? (p.a + row * p.lda + kk) : p.a;
-            cp_async16(dst + (i * 128 + tid) * 16, src, ok ? 16u : 0u);
+        for (int i = 0; i < PIECES; ++i) {
+            const bool ok = kok && (row0 + my_r + i * (NT / 8) < p.n);
+            cp_async16(dst + i * NT * 16, ok ? (base + (int64_t)i * (NT / 8) * p.lda) : p.a, ok ? 16u : 0u);
         }
     };
     if (p.use_async) {
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
 
     // ---- resident B operand: hi/lo panels of W (fwd: B[n][r] = W[n, r]; bwd: B[n = k_in][r = o] = W[o, k_in])
     if (!BWD) {
-        for (int e = tid; e < p.n_pad * p.kred_pad; e += 128) {
+        for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
             const int nn = e / p.kred_pad, r = e - nn * p.kred_pad;       // consecutive threads: consecutive r
             float v = 0.0f;
             if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)nn * p.k + r);
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
             *reinterpret_cast<float*>(b_lo + off) = lo;
         }
     } else {
-        for (int e = tid; e < p.n_pad * p.kred_pad; e += 128) {
+        for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
             const int r = e / p.n_pad, nn = e - r * p.n_pad;              // consecutive threads: consecutive k_in
             float v = 0.0f;
             if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)r * p.k + nn);
@@ -279,19 +283,21 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
         }
         // the MMAs that last read operand stage s (chunk g-2) must have retired
         if (g >= A_STAGES) mbar_wait(&empty_bar[s], ((g >> 1) - 1) & 1);
-        const uint8_t* rs = raw + (g % RAW_STAGES) * RAW_STAGE;
+        const uint8_t* rs = raw + (g % RAW_STAGES) * RAW_STAGE + tid * 16;
+        const int kk = k0 + my_q * 4;
+        const bool tail = k0 + CHUNK > p.kred;              // only the last chunk has columns to mask
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = i * 16 + (tid >> 3);
-            const int q = tid & 7;
-            const int kk = k0 + q * 4;
+        for (int i = 0; i < PIECES; ++i) {
+            const int r = i * (NT / 8) + my_r;
             float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (p.use_async) {
-                const float4 t = *reinterpret_cast<const float4*>(rs + (i * 128 + tid) * 16);
+                const float4 t = *reinterpret_cast<const float4*>(rs + i * NT * 16);
                 v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                if (tail) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (kk + j >= p.kred) v[j] = 0.0f;
+                    for (int j = 0; j < 4; ++j)
+                        if (kk + j >= p.kred) v[j] = 0.0f;
+                }
             } else {
                 const int64_t row = row0 + r;
                 if (row < p.n) {
@@ -307,8 +313,8 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
             }
             float4 h, l;
             split(v[0], h.x, l.x); split(v[1], h.y, l.y); split(v[2], h.z, l.z); split(v[3], h.w, l.w);
-            *reinterpret_cast<float4*>(a_hi + q * A_PANEL + r * 16) = h;
-            *reinterpret_cast<float4*>(a_lo + q * A_PANEL + r * 16) = l;
+            *reinterpret_cast<float4*>(a_hi + my_q * A_PANEL + r * 16) = h;
+            *reinterpret_cast<float4*>(a_lo + my_q * A_PANEL + r * 16) = l;
         }
         fence_async_proxy();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
@@ -336,9 +342,10 @@ __global__ void __launch_bounds__(128) tc_linear_kernel(const Params p) {
         // ---- epilogue: TMEM -> registers -> global.  thread t = row t = TMEM lane t
         mbar_wait(accum_bar, tl & 1);
         tc_fence_after();
-        const int64_t row = row0 + tid;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        const int64_t row = row0 + (tid & 127);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        // warps w and w+4 share lane quadrant w: they take alternate 16-column groups
+        for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
             uint32_t r0[16], r1[16];
             tmem_ld16(lane_addr + (uint32_t)c0, r0);
             tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
@@ -431,7 +438,7 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
     const int ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
     int64_t grid = 148 * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    tc_linear_kernel<BWD><<<(unsigned)grid, 128, smem, st>>>(p);
+    tc_linear_kernel<BWD><<<(unsigned)grid, NT, smem, st>>>(p);
     return check_launch(what);
 }
 
@@ -471,7 +478,7 @@ struct WParams {
     int tmem_cols;
 };
 
-__global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
+__global__ void __launch_bounds__(NT) tc_wgrad_kernel(const WParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int a_panel = 128 * 16 + 16;                     // 2064
     const int b_panel = p.n_pad * 16 + 16;
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     }
     // operand buffers start as zeros: padding features / columns never hold NaN bit patterns
-    for (int i = tid * 16; i < 2 * a_bytes + 2 * b_bytes; i += 128 * 16)
+    for (int i = tid * 16; i < 2 * a_bytes + 2 * b_bytes; i += NT * 16)
         *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const int64_t n_tiles = (p.n + WROWS - 1) / WROWS;
@@ -510,13 +517,13 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
         const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * WROWS;
         uint8_t* dx = raw + (t % p.raw_stages) * raw_stage;
         uint8_t* dzs = dx + rawx_bytes;
-        for (int e = tid; e < WROWS * xq; e += 128) {
+        for (int e = tid; e < WROWS * xq; e += NT) {
             const int r = e / xq, q = e - r * xq;
             const int64_t row = row0 + r;
             const bool ok = (row < p.n) && (q * 4 < p.k);
             cp_async16(dx + e * 16, ok ? (p.x + row * p.ldx + q * 4) : p.x, ok ? 16u : 0u);
         }
-        for (int e = tid; e < WROWS * zq; e += 128) {
+        for (int e = tid; e < WROWS * zq; e += NT) {
             const int r = e / zq, q = e - r * zq;
             const int64_t row = row0 + r;
             const bool ok = (row < p.n) && (q * 4 < p.n_out);
@@ -544,7 +551,7 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
         const float* rx = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage);
         const float* rz = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage + rawx_bytes);
         // ---- A = X^T: item (rq, f): rows 4rq..4rq+3 of feature f -> one 16-byte k group
-        for (int e = tid; e < RQ * p.k_pad4; e += 128) {
+        for (int e = tid; e < RQ * p.k_pad4; e += NT) {
             const int rq = e / p.k_pad4, f = e - rq * p.k_pad4;
             float4 h, l;
             if (f < p.k) {
@@ -561,7 +568,7 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
             *reinterpret_cast<float4*>(a_lo + off) = l;
         }
         // ---- B = dZ^T
-        for (int e = tid; e < RQ * p.n_pad; e += 128) {
+        for (int e = tid; e < RQ * p.n_pad; e += NT) {
             const int rq = e / p.n_pad, o = e - rq * p.n_pad;
             float4 h, l;
             if (o < p.n_out) {
@@ -610,9 +617,9 @@ __global__ void __launch_bounds__(128) tc_wgrad_kernel(const WParams p) {
         tc_fence_after();
         // flush: lane f of block mb holds dW^T[mb*128 + f, :]
         for (int mb = 0; mb < p.m_blocks; ++mb) {
-            const int f = mb * 128 + tid;
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * 2 * p.n_pad);
-            for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+            const int f = mb * 128 + (tid & 127);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * 2 * p.n_pad);
+            for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
                 uint32_t r0[16], r1[16];
                 tmem_ld16(lane_addr + (uint32_t)c0, r0);
                 tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
@@ -704,6 +711,6 @@ extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const floa
     const int ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
     int64_t grid = 148 * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    tc_wgrad_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(p);
+    tc_wgrad_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(p);
     return emer::check_launch("emer_linear_tc_bwd_weight");
 }

@@ -132,7 +132,7 @@ def test_field_and_compositing_at_reference_samples(case):
             assert rel_err(out[k], want[k]) < (1e-4 if k == "depth" else 2e-5), (k, rel_err(out[k], want[k]))
     for k in ("density", "static_density", "dynamic_density", "forward_flow", "weights"):
         if k in want["extras"] and k in out["extras"]:
-            assert rel_err(out["extras"][k], want["extras"][k]) < 2e-5, (k, rel_err(out["extras"][k], want["extras"][k]))
+            assert rel_err(out["extras"][k], want["extras"][k]) < 5e-5, (k, rel_err(out["extras"][k], want["extras"][k]))
 
 
 def test_image_shaped_batches_round_trip():
