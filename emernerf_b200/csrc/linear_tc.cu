@@ -176,28 +176,35 @@ struct Params {
     int accumulate;       // bwd: dX += result
     int tmem_cols;        // power of two >= 2*n_pad
     int use_async;        // cp.async ring (16-byte aligned rows, no act' in the loader)
+    int a_stages, raw_stages;   // ring depths chosen by the host
+    long long* dbg;       // optional phase timers (cycles) of CTA 0 / thread 0; NULL in production
 };
 
-template <bool BWD>
+// a_stages in {1, 2} operand stages, raw_stages in {2, 4} cp.async stages (host picks the pair that
+// lets the most CTAs share an SM: the kernel is instruction-latency bound per CTA, co-resident
+// CTAs fill each other's bubbles).
+template <bool BWD, int ACT>
 __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [B_hi | B_lo | A ring: A_STAGES x (hi, lo) | raw ring | barriers]
+    // layout: [B_hi | B_lo | A ring: a_stages x (hi, lo) | raw ring | bias | barriers]
     const int b_panel = p.n_pad * 16;
     const int b_bytes = (p.kred_pad / 4) * b_panel;
     uint8_t* b_hi = smem;
     uint8_t* b_lo = smem + b_bytes;
     uint8_t* a_ring = smem + 2 * b_bytes;
-    uint8_t* raw = a_ring + A_STAGES * 2 * A_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + (p.use_async ? RAW_STAGES * RAW_STAGE : 0));
-    uint64_t* empty_bar = bars;                  // [A_STAGES]
-    uint64_t* accum_bar = bars + A_STAGES;       // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + A_STAGES + 1);
+    uint8_t* raw = a_ring + 2 * 2 * A_STAGE;            // the ring area is always 2 stages (epilogue staging)
+    float* bias_s = reinterpret_cast<float*>(raw + (p.use_async ? p.raw_stages * RAW_STAGE : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
+    uint64_t* empty_bar = bars;                  // [2]
+    uint64_t* accum_bar = bars + 2;              // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < A_STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        mbar_init(&empty_bar[0], 1);
+        mbar_init(&empty_bar[1], 1);
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -209,29 +216,35 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
     const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int total = my_tiles * n_chunks;
+    const int a_stages = p.a_stages, raw_stages = p.raw_stages;
 
-    // cp.async producer: chunk g -> raw stage g % RAW_STAGES.  Thread t copies, for i in 0..3, the
+    // cp.async producer: chunk (tile tl, k-chunk c) -> raw stage.  Thread t copies, for i in 0..3, the
     // 16 bytes (row = i*32 + t/8, quad = t%8) into its own slot (i*NT + t): a row's 128 B are read
     // by 8 consecutive threads (coalesced) and the slots of a warp are contiguous (conflict-free).
     constexpr int PIECES = ROWS * (CHUNK / 4) / NT;     // 4
     const int my_r = tid >> 3, my_q = tid & 7;
-    auto issue = [&](int g) {
-        const int tl = g / n_chunks, c = g - tl * n_chunks;
-        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * ROWS;
-        const int kk = c * CHUNK + my_q * 4;
-        const bool kok = kk < p.kred;
-        const float* base = p.a + (row0 + my_r) * p.lda + kk;
-        uint8_t* dst = raw + (g % RAW_STAGES) * RAW_STAGE + tid * 16;
+    const int64_t piece_stride = (int64_t)(NT / 8) * p.lda;          // 32 rows down
+    const float* thread_base = p.a + (int64_t)my_r * p.lda + my_q * 4;
+    int i_tl = 0, i_c = 0, i_stage = 0;                  // next chunk to issue (running counters: no division)
+    auto issue_next = [&]() {
+        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i_tl * gridDim.x) * ROWS;
+        const bool kok = i_c * CHUNK + my_q * 4 < p.kred;
+        const float* src = thread_base + row0 * p.lda + i_c * CHUNK;
+        uint8_t* dst = raw + i_stage * RAW_STAGE + tid * 16;
+        const int64_t rows_left = p.n - row0 - my_r;
 #pragma unroll
         for (int i = 0; i < PIECES; ++i) {
-            const bool ok = kok && (row0 + my_r + i * (NT / 8) < p.n);
-            cp_async16(dst + i * NT * 16, ok ? (base + (int64_t)i * (NT / 8) * p.lda) : p.a, ok ? 16u : 0u);
+            const bool ok = kok && (i * (NT / 8) < rows_left);
+            cp_async16(dst + i * NT * 16, ok ? src : p.a, ok ? 16u : 0u);
+            src += piece_stride;
         }
+        if (++i_c == n_chunks) { i_c = 0; ++i_tl; }
+        if (++i_stage == raw_stages) i_stage = 0;
     };
+    int issued = 0;
     if (p.use_async) {
-#pragma unroll
-        for (int g = 0; g < RAW_STAGES - 1; ++g) {
-            if (g < total) issue(g);
+        for (int g = 0; g < raw_stages - 1; ++g) {
+            if (issued < total) { issue_next(); ++issued; }
             cp_async_commit();
         }
     }
@@ -248,6 +261,7 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
             *reinterpret_cast<float*>(b_hi + off) = hi;
             *reinterpret_cast<float*>(b_lo + off) = lo;
         }
+        for (int e = tid; e < 256; e += NT) bias_s[e] = (p.bias && e < p.ncols) ? __ldg(p.bias + e) : 0.0f;
     } else {
         for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
             const int r = e / p.n_pad, nn = e - r * p.n_pad;              // consecutive threads: consecutive k_in
@@ -268,22 +282,44 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
     const uint32_t idesc = make_idesc(128, p.n_pad);
     const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
     const bool vec_m = p.relu_src && (p.ld_relu % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.relu_src) & 15) == 0);
+    // descriptor templates: only the 14-bit start-address field changes between MMAs
+    const uint64_t desc_a = make_desc(0, A_PANEL, 128);
+    const uint64_t desc_b = make_desc(0, b_panel, 128);
+    const uint32_t a_ring_addr = smem_u32(a_ring) >> 4;
+    const uint32_t b_hi_addr = smem_u32(b_hi) >> 4, b_lo_addr = smem_u32(b_lo) >> 4;
 
+    const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = timing ? clock64() : 0;
+#define TC_TICK(slot)                      \
+    if (timing) {                          \
+        const long long t_now = clock64(); \
+        tm[slot] += t_now - t_prev;        \
+        t_prev = t_now;                    \
+    }
+    int tl = 0, c = 0, rstage = 0;
+    uint32_t use0 = 0, use1 = 0;                 // fills of operand stage 0 / 1
     for (int g = 0; g < total; ++g) {
-        const int tl = g / n_chunks, c = g - tl * n_chunks;
         const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * ROWS;
         const int k0 = c * CHUNK;
-        const int s = g & 1;
+        const int s = (a_stages == 2) ? (g & 1) : 0;
         uint8_t* a_hi = a_ring + (s * 2) * A_STAGE;
         uint8_t* a_lo = a_hi + A_STAGE;
         if (p.use_async) {
-            if (g + RAW_STAGES - 1 < total) issue(g + RAW_STAGES - 1);
+            if (issued < total) { issue_next(); ++issued; }
             cp_async_commit();
-            cp_async_wait<RAW_STAGES - 1>();          // this thread's pieces of chunk g have landed
+            TC_TICK(0)
+            if (raw_stages == 4) cp_async_wait<3>();
+            else cp_async_wait<1>();                   // this thread's pieces of chunk g have landed
         }
-        // the MMAs that last read operand stage s (chunk g-2) must have retired
-        if (g >= A_STAGES) mbar_wait(&empty_bar[s], ((g >> 1) - 1) & 1);
-        const uint8_t* rs = raw + (g % RAW_STAGES) * RAW_STAGE + tid * 16;
+        TC_TICK(1)
+        // the MMAs that last read operand stage s must have retired
+        {
+            const uint32_t uses = s ? use1 : use0;
+            if (uses > 0) mbar_wait(&empty_bar[s], (uses - 1) & 1);
+        }
+        TC_TICK(2)
+        const uint8_t* rs = raw + rstage * RAW_STAGE + tid * 16;
         const int kk = k0 + my_q * 4;
         const bool tail = k0 + CHUNK > p.kred;              // only the last chunk has columns to mask
 #pragma unroll
@@ -316,92 +352,130 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
             *reinterpret_cast<float4*>(a_hi + my_q * A_PANEL + r * 16) = h;
             *reinterpret_cast<float4*>(a_lo + my_q * A_PANEL + r * 16) = l;
         }
+        TC_TICK(3)
         fence_async_proxy();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();
+        TC_TICK(4)
         if (tid == 0) {
             tc_fence_after();
             const int ksteps = min(CHUNK, p.kred_pad - k0) / 8;
+            const uint32_t a_hi_addr = a_ring_addr + (uint32_t)((s * 2) * A_STAGE >> 4);
+            const uint32_t a_lo_addr = a_hi_addr + (uint32_t)(A_STAGE >> 4);
+            const uint32_t b_off = (uint32_t)((k0 >> 2) * b_panel) >> 4;
+            const uint32_t d1 = tmem_base + (uint32_t)p.n_pad;
+#pragma unroll 4
             for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t a_off = (uint32_t)(ks * 2) * A_PANEL;
-                const uint32_t b_off = (uint32_t)((k0 >> 2) + ks * 2) * b_panel;
-                const uint64_t da_hi = make_desc(smem_u32(a_hi) + a_off, A_PANEL, 128);
-                const uint64_t da_lo = make_desc(smem_u32(a_lo) + a_off, A_PANEL, 128);
-                const uint64_t db_hi = make_desc(smem_u32(b_hi) + b_off, b_panel, 128);
-                const uint64_t db_lo = make_desc(smem_u32(b_lo) + b_off, b_panel, 128);
+                const uint32_t ao = (uint32_t)(ks * 2 * A_PANEL) >> 4;
+                const uint32_t bo = b_off + ((uint32_t)(ks * 2 * b_panel) >> 4);
+                const uint64_t da_hi = desc_a | (uint64_t)(a_hi_addr + ao);
+                const uint64_t da_lo = desc_a | (uint64_t)(a_lo_addr + ao);
+                const uint64_t db_hi = desc_b | (uint64_t)(b_hi_addr + bo);
+                const uint64_t db_lo = desc_b | (uint64_t)(b_lo_addr + bo);
                 const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
-                mma_tf32(tmem_base, da_hi, db_hi, idesc, first);                       // chain 0
-                mma_tf32(tmem_base + (uint32_t)p.n_pad, da_lo, db_hi, idesc, first);   // chain 1
-                mma_tf32(tmem_base + (uint32_t)p.n_pad, da_hi, db_lo, idesc, 1u);
+                mma_tf32(tmem_base, da_hi, db_hi, idesc, first);      // chain 0
+                mma_tf32(d1, da_lo, db_hi, idesc, first);             // chain 1
+                mma_tf32(d1, da_hi, db_lo, idesc, 1u);
             }
             tc_commit(&empty_bar[s]);                        // operand stage reusable once these retire
             if (c == n_chunks - 1) tc_commit(accum_bar);     // ... and the tile's accumulators are complete
         }
-        if (c != n_chunks - 1) continue;
+        if (s) ++use1; else ++use0;
+        if (++rstage == raw_stages) rstage = 0;
+        TC_TICK(5)
+        const bool last_chunk = (c == n_chunks - 1);
+        const int tile_idx = tl;
+        if (++c == n_chunks) { c = 0; ++tl; }
+        if (!last_chunk) continue;
 
-        // ---- epilogue: TMEM -> registers -> global.  thread t = row t = TMEM lane t
-        mbar_wait(accum_bar, tl & 1);
+        // ---- epilogue: TMEM -> registers -> (bias, activation) -> shared staging -> coalesced global.
+        // All MMAs of the tile have retired, so the operand ring doubles as the staging buffer.
+        mbar_wait(accum_bar, tile_idx & 1);
         tc_fence_after();
-        const int64_t row = row0 + (tid & 127);
+        TC_TICK(6)
+        float* stage = reinterpret_cast<float*>(a_ring);
+        constexpr int SLD = 64 + 4;                          // staging row stride (floats): conflict-free
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        // warps w and w+4 share lane quadrant w: they take alternate 16-column groups
-        for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
-            uint32_t r0[16], r1[16];
-            tmem_ld16(lane_addr + (uint32_t)c0, r0);
-            tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
-            tmem_ld_wait();
-            if (row < p.n && c0 < p.ncols) {
-                float* out = p.c + row * p.ldc + c0;
+        const int my_row = tid & 127;
+        for (int cb = 0; cb < p.n_pad; cb += 64) {           // 64-column blocks
+            const int cw = min(64, p.n_pad - cb);
+            // warps w and w+4 share lane quadrant w: they take alternate 16-column groups
+            for (int c0 = (warp >> 2) * 16; c0 < cw; c0 += 32) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(lane_addr + (uint32_t)(cb + c0), r0);
+                tmem_ld16(lane_addr + (uint32_t)(p.n_pad + cb + c0), r1);
+                tmem_ld_wait();
+                float* dstp = stage + my_row * SLD + c0;
 #pragma unroll
                 for (int j0 = 0; j0 < 16; j0 += 4) {
-                    if (c0 + j0 >= p.ncols) break;
                     float o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int col = c0 + j0 + j;
                         float v = __uint_as_float(r0[j0 + j]) + __uint_as_float(r1[j0 + j]);
                         if (!BWD) {
-                            if (p.bias && col < p.ncols) v += __ldg(p.bias + col);
-                            v = act_fwd(v, p.act);
+                            v += bias_s[cb + c0 + j0 + j];
+                            if (ACT == EMER_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+                            if (ACT == EMER_ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
                         }
                         o[j] = v;
                     }
-                    const bool full = c0 + j0 + 3 < p.ncols;
-                    if (BWD && p.relu_src && c0 + j0 < p.relu_cols) {
-                        const float* m = p.relu_src + row * p.ld_relu + c0 + j0;
-                        if (vec_m && full && c0 + j0 + 3 < p.relu_cols) {
-                            const float4 mm = __ldg(reinterpret_cast<const float4*>(m));
-                            if (!(mm.x > 0.0f)) o[0] = 0.0f;
-                            if (!(mm.y > 0.0f)) o[1] = 0.0f;
-                            if (!(mm.z > 0.0f)) o[2] = 0.0f;
-                            if (!(mm.w > 0.0f)) o[3] = 0.0f;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (c0 + j0 + j < p.ncols && c0 + j0 + j < p.relu_cols && !(__ldg(m + j) > 0.0f)) o[j] = 0.0f;
-                        }
-                    }
-                    if (vec_c && full) {
-                        float4* dst = reinterpret_cast<float4*>(out + j0);
-                        if (BWD && p.accumulate) {
-                            const float4 old = *dst;
-                            o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
-                        }
-                        *dst = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(dstp + j0) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            __syncthreads();
+            // copy-out: consecutive threads write consecutive 16-byte pieces of a row
+            const int q_per_row = cw / 4;
+            for (int e = tid; e < ROWS * q_per_row; e += NT) {
+                const int r = e / q_per_row, q = e - r * q_per_row;
+                const int64_t row = row0 + r;
+                const int col = cb + q * 4;
+                if (row >= p.n || col >= p.ncols) continue;
+                float4 v = *reinterpret_cast<const float4*>(stage + r * SLD + q * 4);
+                float o[4] = {v.x, v.y, v.z, v.w};
+                const bool full = col + 3 < p.ncols;
+                if (BWD && p.relu_src && col < p.relu_cols) {
+                    const float* m = p.relu_src + row * p.ld_relu + col;
+                    if (vec_m && full && col + 3 < p.relu_cols) {
+                        const float4 mm = __ldg(reinterpret_cast<const float4*>(m));
+                        if (!(mm.x > 0.0f)) o[0] = 0.0f;
+                        if (!(mm.y > 0.0f)) o[1] = 0.0f;
+                        if (!(mm.z > 0.0f)) o[2] = 0.0f;
+                        if (!(mm.w > 0.0f)) o[3] = 0.0f;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (c0 + j0 + j < p.ncols) {
-                                if (BWD && p.accumulate) o[j] += out[j0 + j];
-                                out[j0 + j] = o[j];
-                            }
+                        for (int j = 0; j < 4; ++j)
+                            if (col + j < p.ncols && col + j < p.relu_cols && !(__ldg(m + j) > 0.0f)) o[j] = 0.0f;
+                    }
+                }
+                float* out = p.c + row * p.ldc + col;
+                if (vec_c && full) {
+                    if (BWD && p.accumulate) {
+                        const float4 old = *reinterpret_cast<const float4*>(out);
+                        o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+                    }
+                    *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (col + j < p.ncols) {
+                            if (BWD && p.accumulate) o[j] += out[j];
+                            out[j] = o[j];
                         }
                     }
                 }
             }
+            __syncthreads();         // staging buffer free (next block / next tile's operands)
         }
-        tc_fence_before();      // TMEM reads done before the next tile's first MMA overwrites the accumulators
+        tc_fence_before();           // TMEM reads done before the next tile's first MMA overwrites the accumulators
         __syncthreads();
+        TC_TICK(7)
+    }
+#undef TC_TICK
+    if (timing) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p.dbg[i] = tm[i];
+        p.dbg[8] = total;
+        p.dbg[9] = my_tiles;
     }
     if (p.use_async) cp_async_wait<0>();
     tc_fence_before();
@@ -410,9 +484,26 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static long long* g_tc_dbg = nullptr;
+
+template <bool BWD, int ACT>
+static int launch_t(Params& p, size_t smem, int64_t grid, cudaStream_t st, const char* what) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BWD, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("%s: cudaFuncSetAttribute(%zu): %s", what, smem, cudaGetErrorString(e));
+            return -2;
+        }
+        configured = smem;
+    }
+    tc_linear_kernel<BWD, ACT><<<(unsigned)grid, NT, smem, st>>>(p);
+    return check_launch(what);
+}
 
 template <bool BWD>
 static int launch(Params& p, cudaStream_t st, const char* what) {
+    p.dbg = g_tc_dbg;
     p.kred = BWD ? p.n_out : p.k;
     p.ncols = BWD ? p.k : p.n_out;
     p.kred_pad = round_up(p.kred, 8);
@@ -420,26 +511,36 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
     EMER_REQUIRE(p.n_pad <= 256, "%s: output width %d exceeds one MMA (256)", what, p.ncols);
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.n_pad) p.tmem_cols *= 2;
-    const size_t base = (size_t)2 * (p.kred_pad / 4) * p.n_pad * 16 + (size_t)A_STAGES * 2 * A_STAGE + (A_STAGES + 1) * 8 + 16;
-    p.use_async = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0) && !(BWD && p.act != EMER_ACT_NONE) &&
-                  (base + (size_t)RAW_STAGES * RAW_STAGE <= 227 * 1024);
-    const size_t smem = base + (p.use_async ? (size_t)RAW_STAGES * RAW_STAGE : 0);
-    EMER_REQUIRE(smem <= 227 * 1024, "%s: layer %dx%d needs %zu B of shared memory", what, p.k, p.n_out, smem);
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[BWD]) {
-        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("%s: cudaFuncSetAttribute(%zu): %s", what, smem, cudaGetErrorString(e));
-            return -2;
+    const size_t fixed = (size_t)2 * (p.kred_pad / 4) * p.n_pad * 16 + (size_t)2 * 2 * A_STAGE + 256 * 4 + 3 * 8 + 16;
+    const bool can_async = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0) &&
+                           !(BWD && p.act != EMER_ACT_NONE);
+    // prefer the configuration that fits the most CTAs per SM
+    p.use_async = 0; p.a_stages = 2; p.raw_stages = 4;
+    size_t smem = fixed;
+    int ctas_per_sm = 1;
+    if (can_async) {
+        const size_t small = fixed + 2 * RAW_STAGE, big = fixed + 4 * RAW_STAGE;
+        if (small <= 113 * 1024) {
+            p.use_async = 1; p.a_stages = 2; p.raw_stages = 2; smem = small;
+            ctas_per_sm = small <= 75 * 1024 ? 3 : 2;
+        } else if (big <= 227 * 1024) {
+            p.use_async = 1; p.a_stages = 2; p.raw_stages = 4; smem = big;
+        } else if (small <= 227 * 1024) {
+            p.use_async = 1; p.a_stages = 2; p.raw_stages = 2; smem = small;
         }
-        configured[BWD] = smem;
+    } else {
+        ctas_per_sm = fixed <= 75 * 1024 ? 3 : (fixed <= 113 * 1024 ? 2 : 1);
     }
+    EMER_REQUIRE(smem <= 227 * 1024, "%s: layer %dx%d needs %zu B of shared memory", what, p.k, p.n_out, smem);
+    // TMEM: co-resident CTAs share 512 columns
+    while (ctas_per_sm > 1 && ctas_per_sm * p.tmem_cols > 512) --ctas_per_sm;
     const int64_t n_tiles = ceil_div(p.n, ROWS);
-    const int ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
     int64_t grid = 148 * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    tc_linear_kernel<BWD><<<(unsigned)grid, NT, smem, st>>>(p);
-    return check_launch(what);
+    if (BWD) return launch_t<true, 0>(p, smem, grid, st, what);
+    if (p.act == EMER_ACT_RELU) return launch_t<false, EMER_ACT_RELU>(p, smem, grid, st, what);
+    if (p.act == EMER_ACT_SIGMOID) return launch_t<false, EMER_ACT_SIGMOID>(p, smem, grid, st, what);
+    return launch_t<false, EMER_ACT_NONE>(p, smem, grid, st, what);
 }
 
 }  // namespace tc
@@ -594,15 +695,19 @@ __global__ void __launch_bounds__(NT) tc_wgrad_kernel(const WParams p) {
         cp_async_commit();
         if (tid == 0) {
             tc_fence_after();
+            const uint64_t desc_a = make_desc(0, a_panel, 128), desc_b = make_desc(0, b_panel, 128);
+            const uint32_t a_hi_addr = smem_u32(a_hi) >> 4, a_lo_addr = smem_u32(a_lo) >> 4;
+            const uint32_t b_hi_addr = smem_u32(b_hi) >> 4, b_lo_addr = smem_u32(b_lo) >> 4;
+#pragma unroll
             for (int ks = 0; ks < WROWS / 8; ++ks) {
-                const uint32_t boff = (uint32_t)(ks * 2) * b_panel;
-                const uint64_t db_hi = make_desc(smem_u32(b_hi) + boff, b_panel, 128);
-                const uint64_t db_lo = make_desc(smem_u32(b_lo) + boff, b_panel, 128);
+                const uint32_t bo = (uint32_t)(ks * 2 * b_panel) >> 4;
+                const uint64_t db_hi = desc_b | (uint64_t)(b_hi_addr + bo);
+                const uint64_t db_lo = desc_b | (uint64_t)(b_lo_addr + bo);
                 const uint32_t acc = (t == 0 && ks == 0) ? 0u : 1u;
                 for (int mb = 0; mb < p.m_blocks; ++mb) {
-                    const uint32_t aoff = (uint32_t)(mb * RQ + ks * 2) * a_panel;
-                    const uint64_t da_hi = make_desc(smem_u32(a_hi) + aoff, a_panel, 128);
-                    const uint64_t da_lo = make_desc(smem_u32(a_lo) + aoff, a_panel, 128);
+                    const uint32_t ao = (uint32_t)((mb * RQ + ks * 2) * a_panel) >> 4;
+                    const uint64_t da_hi = desc_a | (uint64_t)(a_hi_addr + ao);
+                    const uint64_t da_lo = desc_a | (uint64_t)(a_lo_addr + ao);
                     const uint32_t d0 = tmem_base + (uint32_t)(mb * 2 * p.n_pad);
                     mma_tf32(d0, da_hi, db_hi, idesc, acc);                           // chain 0
                     mma_tf32(d0 + (uint32_t)p.n_pad, da_lo, db_hi, idesc, acc);       // chain 1
@@ -646,6 +751,13 @@ __global__ void __launch_bounds__(NT) tc_wgrad_kernel(const WParams p) {
 }  // namespace emer
 
 using namespace emer;
+
+/* debugging hook (not part of the product ABI): device buffer of 10 int64 that CTA 0 of the next
+ * tc_linear launches fills with per-phase cycle counts; NULL disables. */
+extern "C" int emer_debug_tc_timing(long long* device_buffer) {
+    tc::g_tc_dbg = device_buffer;
+    return 0;
+}
 
 extern "C" int emer_linear_tc_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                                   int64_t n, int k, int n_out, int act, void* stream) {
