@@ -177,6 +177,7 @@ struct Params {
     int tmem_cols;        // power of two >= 2*n_pad
     int use_async;        // cp.async ring (16-byte aligned rows, no act' in the loader)
     int a_stages, raw_stages;   // ring depths chosen by the host
+    int ring_bytes;             // operand ring area (>= the 34 816 B epilogue staging tile)
     long long* dbg;       // optional phase timers (cycles) of CTA 0 / thread 0; NULL in production
 };
 
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
     uint8_t* b_hi = smem;
     uint8_t* b_lo = smem + b_bytes;
     uint8_t* a_ring = smem + 2 * b_bytes;
-    uint8_t* raw = a_ring + 2 * 2 * A_STAGE;            // the ring area is always 2 stages (epilogue staging)
+    uint8_t* raw = a_ring + p.ring_bytes;               // ring area also serves as the epilogue staging tile
     float* bias_s = reinterpret_cast<float*>(raw + (p.use_async ? p.raw_stages * RAW_STAGE : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
     uint64_t* empty_bar = bars;                  // [2]
@@ -511,25 +512,39 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
     EMER_REQUIRE(p.n_pad <= 256, "%s: output width %d exceeds one MMA (256)", what, p.ncols);
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.n_pad) p.tmem_cols *= 2;
-    const size_t fixed = (size_t)2 * (p.kred_pad / 4) * p.n_pad * 16 + (size_t)2 * 2 * A_STAGE + 256 * 4 + 3 * 8 + 16;
+    const size_t w_bytes = (size_t)2 * (p.kred_pad / 4) * p.n_pad * 16;
+    const size_t misc = 256 * 4 + 3 * 8 + 16;
+    const size_t staging = (size_t)ROWS * 68 * 4;                        // epilogue tile: 128 x (64+4) floats
+    const size_t ring1 = staging > (size_t)2 * A_STAGE ? staging : (size_t)2 * A_STAGE;
+    const size_t ring2 = (size_t)2 * 2 * A_STAGE;
     const bool can_async = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0) &&
                            !(BWD && p.act != EMER_ACT_NONE);
-    // prefer the configuration that fits the most CTAs per SM
-    p.use_async = 0; p.a_stages = 2; p.raw_stages = 4;
-    size_t smem = fixed;
+    // The kernel is instruction-latency bound inside one CTA (measured with the phase timers), so
+    // prefer the ring depths that let 2-3 CTAs share an SM; deeper rings only when one CTA fits anyway.
+    struct Cfg { int a, raw; size_t bytes; };
+    Cfg cands[4] = {{1, 2, w_bytes + ring1 + 2 * RAW_STAGE + misc}, {2, 4, w_bytes + ring2 + 4 * RAW_STAGE + misc},
+                    {2, 2, w_bytes + ring2 + 2 * RAW_STAGE + misc}, {1, 2, w_bytes + ring1 + 2 * RAW_STAGE + misc}};
+    size_t smem = 0;
     int ctas_per_sm = 1;
+    p.use_async = 0;
     if (can_async) {
-        const size_t small = fixed + 2 * RAW_STAGE, big = fixed + 4 * RAW_STAGE;
-        if (small <= 113 * 1024) {
-            p.use_async = 1; p.a_stages = 2; p.raw_stages = 2; smem = small;
-            ctas_per_sm = small <= 75 * 1024 ? 3 : 2;
-        } else if (big <= 227 * 1024) {
-            p.use_async = 1; p.a_stages = 2; p.raw_stages = 4; smem = big;
-        } else if (small <= 227 * 1024) {
-            p.use_async = 1; p.a_stages = 2; p.raw_stages = 2; smem = small;
+        if (cands[0].bytes <= 113 * 1024) {
+            p.use_async = 1; p.a_stages = 1; p.raw_stages = 2; p.ring_bytes = (int)ring1; smem = cands[0].bytes;
+            ctas_per_sm = smem <= 75 * 1024 ? 3 : 2;
+        } else {
+            for (int i = 1; i < 4 && !p.use_async; ++i) {
+                if (cands[i].bytes <= 227 * 1024) {
+                    p.use_async = 1; p.a_stages = cands[i].a; p.raw_stages = cands[i].raw;
+                    p.ring_bytes = (int)(cands[i].a == 2 ? ring2 : ring1); smem = cands[i].bytes;
+                }
+            }
         }
-    } else {
-        ctas_per_sm = fixed <= 75 * 1024 ? 3 : (fixed <= 113 * 1024 ? 2 : 1);
+    }
+    if (!p.use_async) {
+        p.a_stages = 2; p.raw_stages = 2; p.ring_bytes = (int)ring2;
+        smem = w_bytes + ring2 + misc;
+        if (smem > 227 * 1024) { p.a_stages = 1; p.ring_bytes = (int)ring1; smem = w_bytes + ring1 + misc; }
+        ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
     }
     EMER_REQUIRE(smem <= 227 * 1024, "%s: layer %dx%d needs %zu B of shared memory", what, p.k, p.n_out, smem);
     // TMEM: co-resident CTAs share 512 columns
