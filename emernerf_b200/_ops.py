@@ -388,6 +388,27 @@ def pdf_resample(vals: Tensor, cdfs: Tensor, n: int, bias: Optional[Tensor], s_m
     return (out_s, out_t, bins) if want_bins else (out_s, out_t)
 
 
+@torch.no_grad()
+def prop_level(prev_s: Tensor, prev_cdf: Tensor, n: int, bias: Optional[Tensor], s_min: float, s_max: float, kind: str,
+               origins: Tensor, dirs: Tensor, aabb: Tensor, unbounded: bool, desc: GridDesc, table: Tensor,
+               w0: Tensor, b0: Tensor, w1: Tensor, b1: Tensor):
+    """One proposal level in one launch (no autograd): returns (s_edges, t_edges, cdf), each [R, n+1]."""
+    _need_cuda(prev_s, prev_cdf, origins, dirs, table)
+    prev_s, prev_cdf = _f32c(prev_s), _f32c(prev_cdf)
+    r, m1 = prev_cdf.shape
+    dev = prev_s.device
+    out_s = torch.empty((r, n + 1), dtype=torch.float32, device=dev)
+    out_t = torch.empty_like(out_s)
+    out_cdf = torch.empty_like(out_s)
+    if bias is not None:
+        bias = _f32c(bias.reshape(-1))
+    _lib.call("emer_prop_level", ctypes.byref(desc.c), _ptr(prev_s), _ptr(prev_cdf), m1, n, _ptr(bias), float(s_min),
+              float(s_max), STOT_KINDS[kind], _ptr(_f32c(origins)), _ptr(_f32c(dirs)), _ptr(_f32c(aabb.reshape(-1))),
+              int(unbounded), _ptr(_f32c(table)), _ptr(_f32c(w0)), _ptr(_f32c(b0)), _ptr(_f32c(w1.reshape(-1))),
+              _ptr(_f32c(b1.reshape(-1))), _ptr(out_s), _ptr(out_t), _ptr(out_cdf), r, _stream())
+    return out_s, out_t, out_cdf
+
+
 # ----------------------------------------------------------------------------- volume rendering
 class _Composite(torch.autograd.Function):
     @staticmethod

@@ -1,0 +1,233 @@
+// One proposal level in ONE launch (no-grad path of PropNetEstimator.sampling):
+//   inverse-CDF resampling of the previous level -> s->t warp -> ray march -> contraction+selector ->
+//   hash grid (3-D, F floats x L levels <= 16 features) -> Linear(LF,64)-ReLU-Linear(64,1) ->
+//   trunc_exp(x-1) -> sigma*delta -> exclusive scan along the ray -> CDF of this level.
+// Replaces, per level, ~15 launches of the modular path (third_party/nerfacc_prop_net.py:147-170 with
+// render_utils.py:314-324 and radiance_field.py:825-841 of the reference) and every intermediate
+// [R,S,*] tensor: the only HBM traffic is the table gathers (L2-resident: 18-22 MB tables) and the
+// [R, n+1] edges / CDF rows.  The resampling arithmetic is the same code as emer_pdf_resample
+// (bit-exact s/t edges); the MLP runs on the FP32 FMA pipe with weights broadcast from shared memory.
+//
+// One warp per ray; lane l owns edges / samples l, l+32, ... (n <= 256).
+#include "common.cuh"
+
+namespace emer {
+
+struct PropParams {
+    emer_grid_desc g;
+    const float* prev_s;      // [R, m1]
+    const float* prev_cdf;    // [R, m1]
+    const float* bias;        // [R] or null (0.5)
+    const float* origins;     // [R, 3]
+    const float* dirs;        // [R, 3]
+    const float* aabb;        // [6]
+    const float* table;
+    const float* w0;          // [64, LF]
+    const float* b0;          // [64]
+    const float* w1;          // [64]
+    const float* b1;          // [1]
+    float* out_s;             // [R, n+1]
+    float* out_t;             // [R, n+1]
+    float* out_cdf;           // [R, n+1]
+    int64_t n_rays;
+    int m1, n, stot_kind, unbounded;
+    float s_min, s_max;
+};
+
+constexpr int PL_WARPS = 8;
+constexpr int PL_MAX_EDGES = 257;
+constexpr int PL_HID = 64;
+constexpr int PL_MAX_IN = 16;
+
+__device__ __forceinline__ float pl_s_to_t(float s, float s_min, float s_max, int kind) {
+    const float v = s * s_max + (1.0f - s) * s_min;
+    switch (kind) {
+        case EMER_STOT_UNIFORM: return v;
+        case EMER_STOT_LINDISP: return 1.0f / v;
+        case EMER_STOT_SQRT: return v * v;
+        case EMER_STOT_LOG: return expf(v);
+        case EMER_STOT_UNIFORM_LINDISP: return v < 0.5f ? v * 400.0f : (1.0f / (2.0f - 2.0f * v)) * 200.0f;
+        default: return v < 0.5f ? 2.0f * v : 1.0f / (2.0f - 2.0f * v);
+    }
+}
+
+// LF_T > 0: compile-time feature count with F = 1 (the shipped proposal grids: 8 levels x 1 feature);
+// LF_T == 0: generic run-time loops.
+template <int LF_T>
+__global__ void __launch_bounds__(PL_WARPS * 32) prop_level_kernel(const PropParams p) {
+    __shared__ float t_edges[PL_WARPS][PL_MAX_EDGES + 3];
+    __shared__ float w0s[PL_HID * PL_MAX_IN];
+    __shared__ float b0s[PL_HID], w1s[PL_HID];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int LF = LF_T > 0 ? LF_T : p.g.n_levels * p.g.n_feat;
+    for (int e = tid; e < PL_HID * LF; e += PL_WARPS * 32) w0s[e] = __ldg(p.w0 + e);
+    for (int e = tid; e < PL_HID; e += PL_WARPS * 32) { b0s[e] = __ldg(p.b0 + e); w1s[e] = __ldg(p.w1 + e); }
+    __syncthreads();
+    const float b1 = __ldg(p.b1);
+    const int64_t ray = (int64_t)blockIdx.x * PL_WARPS + wid;
+    if (ray >= p.n_rays) return;
+    const int n = p.n, m1 = p.m1;
+
+    // ---- 1. inverse-CDF resampling (same arithmetic, same order as pdf_resample_kernel)
+    const float* c = p.prev_cdf + ray * m1;
+    const float* v = p.prev_s + ray * m1;
+    const float u_floor = __ldg(c), u_ceil = __ldg(c + m1 - 1);
+    const float u_step = (u_ceil - u_floor) / (float)n;
+    const float bb = p.bias ? __ldg(p.bias + ray) : 0.5f;
+    for (int k = lane; k <= n; k += 32) {
+        const float u = u_floor + ((float)k + (bb - 0.5f)) * u_step;
+        int lo = 0, hi = m1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(c + mid) > u) hi = mid;
+            else lo = mid + 1;
+        }
+        const int p0 = min(max(lo - 1, 0), m1 - 1), p1 = min(max(lo, 0), m1 - 1);
+        const float u_lo = __ldg(c + p0), u_hi = __ldg(c + p1), t_lo = __ldg(v + p0), t_hi = __ldg(v + p1);
+        const float du = u_hi - u_lo;
+        float s;
+        if (du < 1e-10f) s = (t_lo + t_hi) * 0.5f;
+        else s = (u - u_lo) * ((t_hi - t_lo) / du) + t_lo;
+        const float t = pl_s_to_t(s, p.s_min, p.s_max, p.stot_kind);
+        p.out_s[ray * (n + 1) + k] = s;
+        p.out_t[ray * (n + 1) + k] = t;
+        t_edges[wid][k] = t;
+    }
+    __syncwarp();
+
+    // ---- 2. density at the interval midpoints, 3. scan -> CDF
+    const float ox = __ldg(p.origins + ray * 3), oy = __ldg(p.origins + ray * 3 + 1), oz = __ldg(p.origins + ray * 3 + 2);
+    const float dx = __ldg(p.dirs + ray * 3), dy = __ldg(p.dirs + ray * 3 + 1), dz = __ldg(p.dirs + ray * 3 + 2);
+    float lo3[3], hi3[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { lo3[d] = __ldg(p.aabb + d); hi3[d] = __ldg(p.aabb + 3 + d); }
+    const int L = LF_T > 0 ? LF_T : p.g.n_levels, F = LF_T > 0 ? 1 : p.g.n_feat;
+    float carry = 0.0f;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        const bool ok = k < n;
+        float xdelta = 0.0f;
+        if (ok) {
+            const float t0 = t_edges[wid][k], t1 = t_edges[wid][k + 1];
+            const float tt = t0 + t1;
+            // positions = origins + dirs * (t0 + t1) / 2   (render_utils.py:318)
+            float pos[3] = {ox + dx * tt / 2.0f, oy + dy * tt / 2.0f, oz + dz * tt / 2.0f};
+            // contraction + selector (same operation order as contract_point in elementwise.cu)
+            float xn[3], m = -1.0f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float q = (pos[d] - lo3[d]) / (hi3[d] - lo3[d]);
+                if (p.unbounded) q = q * 2.0f - 1.0f;
+                xn[d] = q;
+                m = fmaxf(m, fabsf(q));
+            }
+            bool sel = true;
+            float xc[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float y;
+                if (p.unbounded) {
+                    y = (m < 1.0f) ? xn[d] : (2.0f - 1.0f / m) * (xn[d] / m);
+                    y = y / 4.0f + 0.5f;
+                } else {
+                    y = xn[d];
+                }
+                xc[d] = y;
+                sel = sel && (y > 0.0f) && (y < 1.0f);
+            }
+            if (!sel) { xc[0] = xc[0] * 0.0f; xc[1] = xc[1] * 0.0f; xc[2] = xc[2] * 0.0f; }
+            // hash grid (3-D), same corner order / fma chain as grid_fwd_kernel
+            float enc[LF_T > 0 ? LF_T : PL_MAX_IN];
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const float scale = p.g.scale[l];
+                const uint32_t res = p.g.resolution[l], off = p.g.offset[l], size = p.g.offset[l + 1] - off;
+                const bool hashed = p.g.hashed[l] != 0;
+                uint32_t c0[3];
+                float w[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float ps = fmaf(scale, xc[d], 0.5f);
+                    const float fl = floorf(ps);
+                    c0[d] = (uint32_t)(int)fl;
+                    w[d] = ps - fl;
+                }
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    float wt = 1.0f;
+                    uint32_t ci[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        if ((cc >> d) & 1) { wt = wt * w[d]; ci[d] = c0[d] + 1u; }
+                        else { wt = wt * (1.0f - w[d]); ci[d] = c0[d]; }
+                    }
+                    uint32_t idx = 0;
+                    if (hashed) {
+                        idx = (ci[0] * 1u) ^ (ci[1] * 2654435761u) ^ (ci[2] * 805459861u);
+                        idx &= (size - 1u);
+                    } else {
+                        uint32_t stride = 1;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+                            if (stride <= size) { idx += ci[d] * stride; stride *= res; }
+                        if (idx >= size) idx %= size;
+                    }
+                    const float* e = p.table + ((size_t)off + idx) * F;
+                    if (LF_T > 0) acc[0] = fmaf(wt, __ldg(e), acc[0]);
+                    else for (int f = 0; f < F; ++f) acc[f] = fmaf(wt, __ldg(e + f), acc[f]);
+                }
+                if (LF_T > 0) enc[l] = acc[0];
+                else for (int f = 0; f < F; ++f) enc[l * F + f] = acc[f];
+            }
+            // Linear(LF, 64) - ReLU - Linear(64, 1) - trunc_exp(. - 1)
+            float raw = b1;
+#pragma unroll 4
+            for (int j = 0; j < PL_HID; ++j) {
+                float h = b0s[j];
+#pragma unroll
+                for (int i = 0; i < LF; ++i) h = fmaf(w0s[j * LF + i], enc[i], h);
+                h = h > 0.0f ? h : 0.0f;
+                raw = fmaf(w1s[j], h, raw);
+            }
+            const float sigma = expf(raw - 1.0f);
+            xdelta = sigma * (t1 - t0);
+        }
+        const float incl = warp_scan_incl(xdelta, lane);
+        const float e_excl = carry + (incl - xdelta);
+        if (ok) p.out_cdf[ray * (n + 1) + k] = 1.0f - expf(-e_excl);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) p.out_cdf[ray * (n + 1) + n] = 1.0f;
+}
+
+}  // namespace emer
+
+using namespace emer;
+
+extern "C" int emer_prop_level(const emer_grid_desc* g, const float* prev_s, const float* prev_cdf, int m1, int n,
+                               const float* bias, float s_min, float s_max, int stot_kind, const float* origins,
+                               const float* dirs, const float* aabb6, int unbounded, const float* table,
+                               const float* w0, const float* b0, const float* w1, const float* b1, float* out_s,
+                               float* out_t, float* out_cdf, int64_t n_rays, void* stream) {
+    if (n_rays == 0) return 0;
+    EMER_REQUIRE(g && prev_s && prev_cdf && origins && dirs && aabb6 && table && w0 && b0 && w1 && b1 && out_s &&
+                     out_t && out_cdf,
+                 "emer_prop_level: NULL pointer");
+    EMER_REQUIRE(g->n_dims == 3, "emer_prop_level: proposal grids are 3-D");
+    EMER_REQUIRE(g->n_levels * g->n_feat <= PL_MAX_IN && g->n_feat <= 4, "emer_prop_level: at most %d grid features",
+                 PL_MAX_IN);
+    EMER_REQUIRE(m1 >= 2 && n >= 1 && n + 1 <= PL_MAX_EDGES, "emer_prop_level: n=%d out of range", n);
+    PropParams p;
+    p.g = *g;
+    p.prev_s = prev_s; p.prev_cdf = prev_cdf; p.bias = bias; p.origins = origins; p.dirs = dirs; p.aabb = aabb6;
+    p.table = table; p.w0 = w0; p.b0 = b0; p.w1 = w1; p.b1 = b1; p.out_s = out_s; p.out_t = out_t; p.out_cdf = out_cdf;
+    p.n_rays = n_rays; p.m1 = m1; p.n = n; p.stot_kind = stot_kind; p.unbounded = unbounded; p.s_min = s_min; p.s_max = s_max;
+    const unsigned blocks = (unsigned)ceil_div(n_rays, PL_WARPS);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lf = g->n_levels * g->n_feat;
+    if (g->n_feat == 1 && lf == 8) prop_level_kernel<8><<<blocks, PL_WARPS * 32, 0, st>>>(p);
+    else if (g->n_feat == 1 && lf == 4) prop_level_kernel<4><<<blocks, PL_WARPS * 32, 0, st>>>(p);
+    else prop_level_kernel<0><<<blocks, PL_WARPS * 32, 0, st>>>(p);
+    return check_launch("emer_prop_level");
+}

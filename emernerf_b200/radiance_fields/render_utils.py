@@ -21,7 +21,7 @@ import torch
 from torch import Tensor
 
 from .. import _ops
-from ..third_party.nerfacc_prop_net import PropNetEstimator
+from ..third_party.nerfacc_prop_net import FusedProposalLevel, PropNetEstimator
 from .radiance_field import DensityField, RadianceField
 
 
@@ -173,8 +173,14 @@ def render_rays(
 
         # late binding on purpose: every level evaluates proposal_networks[-1] (see module docstring)
         last_prop = proposal_networks[-1]
+        level_fns = []
+        for _ in proposal_networks:
+            fn = lambda *args: prop_sigma_fn(*args, last_prop)     # noqa: E731
+            # lets sampling() run the level as one fused kernel when no proposal gradients are needed
+            fn.emer_fused = FusedProposalLevel(rays[key_o], rays[key_d], last_prop)
+            level_fns.append(fn)
         t_starts, t_ends = proposal_estimator.sampling(
-            prop_sigma_fns=[lambda *args: prop_sigma_fn(*args, last_prop) for _ in proposal_networks],
+            prop_sigma_fns=level_fns,
             num_samples=cfg.nerf.sampling.num_samples,
             prop_samples=cfg.nerf.propnet.num_samples_per_prop,
             n_rays=rays[key_o].shape[0],

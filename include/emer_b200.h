@@ -126,6 +126,17 @@ int emer_pdf_resample(const float* vals, const float* cdfs, int m1, int n, const
                       float s_min, float s_max, int stot_kind, float* out_s, float* out_t,
                       int32_t* out_bins, int64_t n_rays, void* stream);
 
+/* One whole proposal level in one launch (no-grad path of PropNetEstimator.sampling,
+ * third_party/nerfacc_prop_net.py:147-170 + render_utils.py:314-324 + radiance_field.py:825-841):
+ * resample n intervals from (prev_s, prev_cdf)[R, m1], s->t warp, march, contraction + selector, 3-D hash
+ * grid, Linear(LF,64)-ReLU-Linear(64,1), trunc_exp(x-1), transmittance scan -> out_cdf[R, n+1].
+ * out_s / out_t [R, n+1] are bit-identical to emer_pdf_resample's. */
+int emer_prop_level(const emer_grid_desc* g, const float* prev_s, const float* prev_cdf, int m1, int n,
+                    const float* bias, float s_min, float s_max, int stot_kind, const float* origins,
+                    const float* dirs, const float* aabb6, int unbounded, const float* table,
+                    const float* w0, const float* b0, const float* w1, const float* b1, float* out_s,
+                    float* out_t, float* out_cdf, int64_t n_rays, void* stream);
+
 /* ---- volume rendering along rays (replaces nerfacc.render_transmittance_from_density /
  *      render_weight_from_density / accumulate_along_rays and the torch cumsum/searchsorted of
  *      radiance_fields/render_utils.py:73-115) ---------------------------------------------- */
