@@ -315,14 +315,21 @@ class _MLPChain(torch.autograd.Function):
                 grads_w[i], grads_b[i] = _layer_bwd_weight(inp, ld, dz, lddz, w, has_bias, n)
             if i == 0 and not need_x:
                 break
-            d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dz.device)
             if i > 0:
+                d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dz.device)
                 h = ws[i - 1].shape[0]          # first h columns of this layer's input are ReLU outputs
                 _layer_bwd_data(dz, lddz, w, d_inp, d_inp.shape[1], n, inp, ld, h)
                 if i == skip_layer:
                     dx_skip = d_inp[:, h:h + k0]
                 dz, lddz = d_inp[:, :h], d_inp.shape[1]
+            elif (dx_skip is not None and _tc_rows_ok(n, k, n_out) and dx_skip.stride(0) % 4 == 0
+                  and dx_skip.data_ptr() % 16 == 0):
+                # accumulate layer 0's input gradient straight into the skip slice (no add pass)
+                _lib.call("emer_linear_tc_bwd_data", _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(w), _ptr(dx_skip),
+                          dx_skip.stride(0), None, 0, 0, n, k, n_out, 1, _stream())
+                dx, dx_skip = dx_skip, None
             else:
+                d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dz.device)
                 _layer_bwd_data(dz, lddz, w, d_inp, d_inp.shape[1], n, None, 0, 0)
                 dx = d_inp[:, :k]
         if need_x:
@@ -366,6 +373,61 @@ def cat_pad4(parts, dim_check: bool = True) -> Tensor:
     if pad == 0:
         return cat
     return torch.nn.functional.pad(cat, (0, pad))[..., :total]
+
+
+# ----------------------------------------------------------------------------- field tail
+FT_DIR = 33
+
+
+class _FieldTail(torch.autograd.Function):
+    """feats [R, S, >=G], per-ray dirs [R, 3], per-ray embedding index [R] -> (sigma [R, S],
+    rgb_in [R, S, G+33+E] laid out [geo | dir encoding | embedding] in rows padded to 16 bytes)."""
+
+    @staticmethod
+    def forward(ctx, feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional[Tensor], g_dim: int):
+        _need_cuda(feats, dirs)
+        r, s_, width_in = feats.shape
+        f2, ldf = _rows(feats, width_in)
+        dirs = _f32c(dirs)
+        e_dim = 0 if emb is None else emb.shape[1]
+        embc = None if emb is None else _f32c(emb)
+        idxc = None if idx is None else idx.to(torch.int64).contiguous()
+        width = g_dim + FT_DIR + e_dim
+        ld = _pad4(width)
+        out = torch.empty((r * s_, ld), dtype=torch.float32, device=feats.device)
+        sigma = torch.empty((r, s_), dtype=torch.float32, device=feats.device)
+        _lib.call("emer_field_tail_fwd", _ptr(f2), ldf, g_dim, _ptr(dirs), _ptr(idxc), _ptr(embc), e_dim, _ptr(out), ld,
+                  _ptr(sigma), r, s_, _stream())
+        ctx.save_for_backward(f2, idxc)
+        ctx.meta = (ldf, g_dim, e_dim, width, ld, r, s_, width_in, None if emb is None else emb.shape)
+        return sigma, out.view(r, s_, ld)[..., :width]
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_rgb_in):
+        f2, idxc = ctx.saved_tensors
+        ldf, g_dim, e_dim, width, ld, r, s_, width_in, emb_shape = ctx.meta
+        n = r * s_
+        if d_rgb_in is None:
+            g2 = torch.zeros((n, ld), dtype=torch.float32, device=f2.device)
+        else:
+            g2 = d_rgb_in.reshape(n, width)
+            if g2.stride(1) != 1 or g2.stride(0) % 4 != 0 or g2.data_ptr() % 16 != 0:
+                g2 = torch.nn.functional.pad(g2, (0, ld - width))
+        ldg = g2.stride(0)
+        d_emb = None
+        if emb_shape is not None and ctx.needs_input_grad[3]:
+            d_emb = torch.zeros(emb_shape, dtype=torch.float32, device=f2.device)
+        ds = None if d_sigma is None else _f32c(d_sigma)
+        _lib.call("emer_field_tail_bwd", _ptr(f2), ldf, _ptr(g2), ldg, g_dim, _ptr(ds), _ptr(idxc), _ptr(d_emb), e_dim, r,
+                  s_, _stream())
+        d_feats = g2[:, :g_dim]
+        if width_in > g_dim:
+            d_feats = torch.nn.functional.pad(d_feats, (0, width_in - g_dim))
+        return d_feats.reshape(r, s_, width_in), None, None, d_emb, None
+
+
+def field_tail(feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional[Tensor], g_dim: int):
+    return _FieldTail.apply(feats, dirs, idx, emb, g_dim)
 
 
 # ----------------------------------------------------------------------------- sampling

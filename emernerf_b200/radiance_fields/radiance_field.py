@@ -190,6 +190,43 @@ class RadianceField(nn.Module):
     def device(self) -> torch.device:
         return self.aabb.device
 
+    # ------------------------------------------------------------------ fused field tail
+    def _tail_inputs(self, directions, data_dict):
+        """(dirs [R,3], idx [R] | None, emb weight | None) when the fused tail applies: default density
+        activation, per-ray view directions / embedding indices handed over as stride-0 per-sample views
+        (what render_rays builds), CUDA tensors.  None -> the general per-point path."""
+        if not (self._fused_density and directions is not None and directions.is_cuda and directions.dim() == 3
+                and directions.stride(1) == 0):
+            return None
+        idx = emb = None
+        if self.enable_cam_embedding or self.enable_img_embedding:
+            if "cam_idx" in data_dict and self.enable_cam_embedding:
+                t = data_dict["cam_idx"]
+            elif "img_idx" in data_dict and self.enable_img_embedding:
+                t = data_dict["img_idx"]
+            else:
+                return None                               # mean-embedding case: general path
+            if not (t.dim() == 2 and t.stride(1) == 0) or self.appearance_embedding_dim > 32:
+                return None
+            idx, emb = t[:, 0], self.appearance_embedding.weight
+        return directions[:, 0], idx, emb
+
+    def _rgb_from_tail(self, rgb_in: Tensor) -> Tensor:
+        """rgb head on a [geo | dir | emb] input: the reference order is [dir | emb | geo]
+        (radiance_field.py:647), so the weight columns that multiply the input are permuted."""
+        G = self.geometry_feature_dim
+        tail = rgb_in.shape[-1] - G
+        key = (G, tail, str(rgb_in.device))
+        if getattr(self, "_perm_key", None) != key:
+            perm = torch.cat([torch.arange(tail, tail + G), torch.arange(0, tail)]).to(rgb_in.device)
+            hid = self.rgb_head.layers[1].weight.shape[1] - (tail + G)
+            self._perm0 = perm
+            self._perm1 = torch.cat([torch.arange(hid, device=rgb_in.device), hid + perm])
+            self._perm_key = key
+        l0, l1, l2 = self.rgb_head.layers
+        return _ops.mlp_chain(rgb_in, [l0.weight[:, self._perm0], l1.weight[:, self._perm1], l2.weight],
+                              [l0.bias, l1.bias, l2.bias], _ops.ACT_SIGMOID, 1)
+
     # ------------------------------------------------------------------ building blocks
     def contract_points(self, positions: Tensor) -> Tensor:
         return _contract_points(positions, self.aabb, self.unbounded)
@@ -248,7 +285,11 @@ class RadianceField(nn.Module):
         G, S = self.geometry_feature_dim, self.semantic_feature_dim
         feats, normed = self.forward_static_hash(positions)
         geo, sem = feats[..., :G], feats[..., G:G + S]
-        static_density = self._density(feats)
+        tail = None if (return_density_only or feats.dim() != 3) else self._tail_inputs(directions, data_dict)
+        if tail is not None:
+            static_density, rgb_in_static = _ops.field_tail(feats, *tail, G)
+        else:
+            static_density = self._density(feats)
 
         dynamic_on = self.dynamic_xyz_encoder is not None and self._has_time(data_dict)
         if dynamic_on:
@@ -264,19 +305,25 @@ class RadianceField(nn.Module):
                 agg["current_dynamic_hash_encodings"] = dyn_enc
                 out.update(agg)
             dyn_geo, dyn_sem = dyn_feats[..., :G], dyn_feats[..., G:G + S]
-            dynamic_density = self._density(dyn_feats)
+            if tail is not None:
+                dynamic_density, rgb_in_dynamic = _ops.field_tail(dyn_feats, *tail, G)
+            else:
+                dynamic_density = self._density(dyn_feats)
             density = static_density + dynamic_density
             out.update(density=density, static_density=static_density, dynamic_density=dynamic_density)
             if return_density_only:
                 return out
-            if directions is not None:
+            if tail is not None:
+                out["dynamic_rgb"] = self._rgb_from_tail(rgb_in_dynamic)
+                out["static_rgb"] = self._rgb_from_tail(rgb_in_static)
+            elif directions is not None:
                 colours = self.query_rgb(directions, geo, dyn_geo, data_dict=data_dict)
                 out["dynamic_rgb"] = colours["dynamic_rgb"]
                 out["static_rgb"] = colours["rgb"]
-                if combine_static_dynamic:
-                    s_ratio = static_density / (density + 1e-6)
-                    d_ratio = dynamic_density / (density + 1e-6)
-                    out["rgb"] = s_ratio[..., None] * out["static_rgb"] + d_ratio[..., None] * out["dynamic_rgb"]
+            if "static_rgb" in out and combine_static_dynamic:
+                s_ratio = static_density / (density + 1e-6)
+                d_ratio = dynamic_density / (density + 1e-6)
+                out["rgb"] = s_ratio[..., None] * out["static_rgb"] + d_ratio[..., None] * out["dynamic_rgb"]
             if self.enable_shadow_head:
                 shadow = run_sequential(self.shadow_head, dyn_geo)
                 out["shadow_ratio"] = shadow
@@ -287,7 +334,9 @@ class RadianceField(nn.Module):
             out["density"] = static_density
             if return_density_only:
                 return out
-            if directions is not None:
+            if tail is not None:
+                out["rgb"] = self._rgb_from_tail(rgb_in_static)
+            elif directions is not None:
                 out["rgb"] = self.query_rgb(directions, geo, data_dict=data_dict)["rgb"]
 
         if self.enable_feature_head and query_feature_head:

@@ -137,6 +137,18 @@ int emer_prop_level(const emer_grid_desc* g, const float* prev_s, const float* p
                     const float* w0, const float* b0, const float* w1, const float* b1, float* out_s,
                     float* out_t, float* out_cdf, int64_t n_rays, void* stream);
 
+/* ---- field tail: between the base MLP and the colour head (radiance_field.py:417-422,622-647) ---
+ * forward : out[n, :] = [feats[n, 0:G] | sinenc((dir[ray]+1)/2) (33) | emb[idx[ray]] (E) | 0-pad]   (ld_out % 4 == 0)
+ *           sigma[n] = exp(feats[n, 0] - 1)     (may be NULL);  n = ray * n_samples + sample
+ * backward: d_out[:, 0] += d_sigma * exp(min(feats0 - 1, 15)) in place (so d_out[:, 0:G] IS d_feats);
+ *           d_emb[idx[ray], :] += sum_s d_out[ray, s, G+33 : G+33+E]  (atomics, caller zeroes; may be NULL) */
+int emer_field_tail_fwd(const float* feats, int64_t ld_feats, int g_dim, const float* dirs,
+                        const int64_t* idx, const float* emb, int e_dim, float* out, int64_t ld_out,
+                        float* sigma, int64_t n_rays, int n_samples, void* stream);
+int emer_field_tail_bwd(const float* feats, int64_t ld_feats, float* d_out, int64_t ld_out, int g_dim,
+                        const float* d_sigma, const int64_t* idx, float* d_emb, int e_dim, int64_t n_rays,
+                        int n_samples, void* stream);
+
 /* ---- volume rendering along rays (replaces nerfacc.render_transmittance_from_density /
  *      render_weight_from_density / accumulate_along_rays and the torch cumsum/searchsorted of
  *      radiance_fields/render_utils.py:73-115) ---------------------------------------------- */
