@@ -27,6 +27,9 @@ _SIGNATURES = {
     "emer_linear_fwd": [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P],
     "emer_linear_bwd_data": [_P, c_int64, _P, c_int64, c_int, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P],
     "emer_linear_bwd_weight": [_P, c_int64, _P, c_int64, _P, c_int64, c_int, _P, _P, c_int64, c_int, c_int, _P],
+    "emer_linear_narrow_fwd": [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P],
+    "emer_linear_narrow_bwd_data": [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int, c_int64, c_int, c_int, _P],
+    "emer_linear_narrow_bwd_weight": [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, _P],
     "emer_linear_tc_fwd": [_P, c_int64, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P],
     "emer_linear_tc_bwd_data": [_P, c_int64, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int64, c_int, c_int64, c_int,
                                 c_int, c_int, _P],
@@ -90,6 +93,12 @@ def tag_of(name: str, args) -> str:
             if name == "emer_grid_bwd":
                 extra = ("_T" if args[4].value else "") + ("_X" if args[5].value else "")
             return f"D{g.n_dims}L{g.n_levels}F{g.n_feat}_N{n}{extra}"
+        if name == "emer_linear_narrow_fwd":
+            return f"k{args[7]}_o{args[8]}_N{args[6]}"
+        if name == "emer_linear_narrow_bwd_data":
+            return f"k{args[9]}_o{args[10]}_N{args[8]}"
+        if name == "emer_linear_narrow_bwd_weight":
+            return f"k{args[7]}_o{args[8]}_N{args[6]}"
         if name in ("emer_linear_tc_fwd",):
             return f"k{args[7]}_o{args[8]}_N{args[6]}"
         if name in ("emer_linear_tc_bwd_data",):

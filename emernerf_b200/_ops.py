@@ -197,8 +197,15 @@ def _aligned(t: Tensor, ld: int) -> bool:
     return ld % 4 == 0 and t.data_ptr() % 16 == 0
 
 
+def _narrow_ok(k: int, n_out: int) -> bool:
+    return LINEAR_IMPL != "simt" and n_out <= 8 and k <= 256
+
+
 def _layer_fwd(x2: Tensor, ldx: int, w: Tensor, b: Optional[Tensor], y: Tensor, ldy: int, n: int, act: int) -> None:
     n_out, k = w.shape
+    if _narrow_ok(k, n_out):
+        _lib.call("emer_linear_narrow_fwd", _ptr(x2), ldx, _ptr(w), _ptr(b), _ptr(y), ldy, n, k, n_out, act, _stream())
+        return
     name = "emer_linear_tc_fwd" if _tc_rows_ok(n, k, n_out) else "emer_linear_fwd"
     _lib.call(name, _ptr(x2), ldx, _ptr(w), _ptr(b), _ptr(y), ldy, n, k, n_out, act, _stream())
 
@@ -207,7 +214,10 @@ def _layer_bwd_data(dz: Tensor, lddz: int, w: Tensor, dx: Tensor, lddx: int, n: 
                     relu_src: Optional[Tensor], ld_relu: int, relu_cols: int) -> None:
     """dx[n, k] = dz[n, n_out] @ w, then dx[:, :relu_cols] *= (relu_src > 0) (the dZ of the layer below)."""
     n_out, k = w.shape
-    if _tc_rows_ok(n, k, n_out):
+    if _narrow_ok(k, n_out):
+        _lib.call("emer_linear_narrow_bwd_data", _ptr(dz), lddz, _ptr(w), _ptr(dx), lddx, _ptr(relu_src), ld_relu,
+                  relu_cols, n, k, n_out, _stream())
+    elif _tc_rows_ok(n, k, n_out):
         _lib.call("emer_linear_tc_bwd_data", _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(w), _ptr(dx), lddx,
                   _ptr(relu_src), ld_relu, relu_cols, n, k, n_out, 0, _stream())
     else:
@@ -223,7 +233,10 @@ def _layer_bwd_weight(x2: Tensor, ldx: int, dz: Tensor, lddz: int, w: Tensor, ha
     db = torch.zeros(n_out, dtype=torch.float32, device=w.device) if has_bias else None
     tc = (_tc_rows_ok(n, k, n_out) and LINEAR_WGRAD_IMPL == "tc" and n_out <= 128 and n_out % 4 == 0
           and _aligned(x2, ldx) and _aligned(dz, lddz) and _pad4(k) <= ldx)
-    if tc:
+    if _narrow_ok(k, n_out):
+        _lib.call("emer_linear_narrow_bwd_weight", _ptr(x2), ldx, _ptr(dz), lddz, _ptr(dw), _ptr(db), n, k, n_out,
+                  _stream())
+    elif tc:
         _lib.call("emer_linear_tc_bwd_weight", _ptr(x2), ldx, _ptr(dz), lddz, _ptr(dw), _ptr(db), n, k, n_out,
                   _stream())
     else:
@@ -322,12 +335,6 @@ class _MLPChain(torch.autograd.Function):
                 if i == skip_layer:
                     dx_skip = d_inp[:, h:h + k0]
                 dz, lddz = d_inp[:, :h], d_inp.shape[1]
-            elif (dx_skip is not None and _tc_rows_ok(n, k, n_out) and dx_skip.stride(0) % 4 == 0
-                  and dx_skip.data_ptr() % 16 == 0):
-                # accumulate layer 0's input gradient straight into the skip slice (no add pass)
-                _lib.call("emer_linear_tc_bwd_data", _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(w), _ptr(dx_skip),
-                          dx_skip.stride(0), None, 0, 0, n, k, n_out, 1, _stream())
-                dx, dx_skip = dx_skip, None
             else:
                 d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dz.device)
                 _layer_bwd_data(dz, lddz, w, d_inp, d_inp.shape[1], n, None, 0, 0)

@@ -248,3 +248,182 @@ extern "C" int emer_linear_bwd_weight(const float* x, int64_t ldx, const float* 
     wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, y, ldy, act, dw, db, n, k, n_out, rows);
     return check_launch("emer_linear_bwd_weight");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Narrow heads (n_out <= 8: rgb 64->3, density 64->1, flow 64->6, shadow 64->1).  These layers are
+// pure streaming: the wide tile kernels waste 8-20x of their tile on padding, so they get
+// memory-bound kernels of their own (weights in shared memory, one pass over the activations).
+namespace emer {
+
+constexpr int NARROW_MAX_OUT = 8;
+constexpr int NARROW_MAX_K = 256;
+
+// Y[row, o] = act(b[o] + sum_k X[row, k] W[o, k]); one thread per row.
+__global__ void __launch_bounds__(256) narrow_fwd_kernel(const float* __restrict__ x, int64_t ldx,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         float* __restrict__ y, int64_t ldy, int64_t n, int k,
+                                                         int n_out, int act) {
+    __shared__ float ws[NARROW_MAX_OUT * NARROW_MAX_K];
+    for (int e = threadIdx.x; e < n_out * k; e += 256) ws[e] = __ldg(w + e);
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    float acc[NARROW_MAX_OUT];
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX_OUT; ++o) acc[o] = (b && o < n_out) ? __ldg(b + o) : 0.0f;
+    const float* xr = x + row * ldx;
+    const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (k % 4 == 0);
+    if (vec) {
+        for (int kk = 0; kk < k; kk += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + kk));
+#pragma unroll
+            for (int o = 0; o < NARROW_MAX_OUT; ++o) {
+                if (o < n_out) {
+                    const float* wo = ws + o * k + kk;
+                    acc[o] = fmaf(v.x, wo[0], acc[o]);
+                    acc[o] = fmaf(v.y, wo[1], acc[o]);
+                    acc[o] = fmaf(v.z, wo[2], acc[o]);
+                    acc[o] = fmaf(v.w, wo[3], acc[o]);
+                }
+            }
+        }
+    } else {
+        for (int kk = 0; kk < k; ++kk) {
+            const float v = __ldg(xr + kk);
+#pragma unroll
+            for (int o = 0; o < NARROW_MAX_OUT; ++o)
+                if (o < n_out) acc[o] = fmaf(v, ws[o * k + kk], acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX_OUT; ++o)
+        if (o < n_out) y[row * ldy + o] = act_fwd(acc[o], act);
+}
+
+// dX[row, k..k+3] = sum_o dZ[row, o] W[o, k..k+3], optionally masked by (relu_src > 0); one thread per
+// (row, 4-column group): consecutive threads write consecutive 16-byte pieces.
+__global__ void __launch_bounds__(256) narrow_bwd_data_kernel(const float* __restrict__ dz, int64_t lddz,
+                                                              const float* __restrict__ w, float* __restrict__ dx,
+                                                              int64_t lddx, const float* __restrict__ relu_src,
+                                                              int64_t ld_relu, int relu_cols, int64_t n, int k,
+                                                              int n_out) {
+    __shared__ float ws[NARROW_MAX_OUT * NARROW_MAX_K];
+    for (int e = threadIdx.x; e < n_out * k; e += 256) ws[e] = __ldg(w + e);
+    __syncthreads();
+    const int groups = (k + 3) / 4;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= n * groups) return;
+    const int64_t row = t / groups;
+    const int c0 = (int)(t - row * groups) * 4;
+    float g[NARROW_MAX_OUT];
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX_OUT; ++o) g[o] = o < n_out ? __ldg(dz + row * lddz + o) : 0.0f;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j;
+        float a = 0.0f;
+        if (c < k) {
+#pragma unroll
+            for (int o = 0; o < NARROW_MAX_OUT; ++o)
+                if (o < n_out) a = fmaf(g[o], ws[o * k + c], a);
+            if (relu_src && c < relu_cols && !(__ldg(relu_src + row * ld_relu + c) > 0.0f)) a = 0.0f;
+        }
+        v[j] = a;
+    }
+    float* out = dx + row * lddx + c0;
+    if ((lddx % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && c0 + 3 < lddx) {
+        *reinterpret_cast<float4*>(out) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c0 + j < k) out[j] = v[j];
+    }
+}
+
+// dW[o, k] += sum_rows dZ[row, o] X[row, k]; db[o] += sum_rows dZ[row, o].
+// Thread t: column c = t % kc (kc = k rounded to 32), row lane t / kc; a CTA walks its row chunk.
+__global__ void __launch_bounds__(256) narrow_wgrad_kernel(const float* __restrict__ x, int64_t ldx,
+                                                           const float* __restrict__ dz, int64_t lddz,
+                                                           float* __restrict__ dw, float* __restrict__ db, int64_t n,
+                                                           int k, int n_out, int64_t rows_per_cta) {
+    __shared__ float red[NARROW_MAX_OUT][256];
+    const int kc = ((k + 31) / 32) * 32;
+    const int lanes = 256 / kc > 0 ? 256 / kc : 1;        // row lanes per CTA (k <= 256)
+    const int c = threadIdx.x % kc, rl = threadIdx.x / kc;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(n, r0 + rows_per_cta);
+    float acc[NARROW_MAX_OUT], bacc[NARROW_MAX_OUT];
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX_OUT; ++o) acc[o] = bacc[o] = 0.0f;
+    if (rl < lanes) {
+        for (int64_t row = r0 + rl; row < r1; row += lanes) {
+            const float xv = c < k ? __ldg(x + row * ldx + c) : 0.0f;
+#pragma unroll
+            for (int o = 0; o < NARROW_MAX_OUT; ++o) {
+                if (o < n_out) {
+                    const float g = __ldg(dz + row * lddz + o);      // broadcast within the warp
+                    acc[o] = fmaf(g, xv, acc[o]);
+                    if (c == 0) bacc[o] += g;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NARROW_MAX_OUT; ++o) red[o][threadIdx.x] = acc[o];
+    __syncthreads();
+    if (threadIdx.x < kc && threadIdx.x < k) {
+        for (int o = 0; o < n_out; ++o) {
+            float s = 0.0f;
+            for (int l = 0; l < lanes; ++l) s += red[o][l * kc + threadIdx.x];
+            atomicAdd(dw + (int64_t)o * k + threadIdx.x, s);
+        }
+    }
+    if (db) {
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < NARROW_MAX_OUT; ++o) red[o][threadIdx.x] = (c == 0 && rl < lanes) ? bacc[o] : 0.0f;
+        __syncthreads();
+        if (threadIdx.x < n_out) {
+            float s = 0.0f;
+            for (int l = 0; l < lanes; ++l) s += red[threadIdx.x][l * kc];
+            atomicAdd(db + threadIdx.x, s);
+        }
+    }
+}
+
+}  // namespace emer
+
+extern "C" int emer_linear_narrow_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y,
+                                      int64_t ldy, int64_t n, int k, int n_out, int act, void* stream) {
+    if (n == 0) return 0;
+    EMER_REQUIRE(x && w && y, "emer_linear_narrow_fwd: NULL pointer");
+    EMER_REQUIRE(n_out >= 1 && n_out <= NARROW_MAX_OUT && k >= 1 && k <= NARROW_MAX_K, "emer_linear_narrow_fwd: k=%d n_out=%d", k, n_out);
+    narrow_fwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, b, y, ldy, n, k, n_out, act);
+    return check_launch("emer_linear_narrow_fwd");
+}
+
+extern "C" int emer_linear_narrow_bwd_data(const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx,
+                                           const float* relu_src, int64_t ld_relu, int relu_cols, int64_t n, int k,
+                                           int n_out, void* stream) {
+    if (n == 0) return 0;
+    EMER_REQUIRE(dz && w && dx, "emer_linear_narrow_bwd_data: NULL pointer");
+    EMER_REQUIRE(n_out >= 1 && n_out <= NARROW_MAX_OUT && k >= 1 && k <= NARROW_MAX_K, "emer_linear_narrow_bwd_data: k=%d n_out=%d", k, n_out);
+    const int64_t total = n * ((k + 3) / 4);
+    narrow_bwd_data_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        dz, lddz, w, dx, lddx, relu_src, ld_relu, relu_src ? relu_cols : 0, n, k, n_out);
+    return check_launch("emer_linear_narrow_bwd_data");
+}
+
+extern "C" int emer_linear_narrow_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
+                                             float* db, int64_t n, int k, int n_out, void* stream) {
+    if (n == 0) return 0;
+    EMER_REQUIRE(x && dz && dw, "emer_linear_narrow_bwd_weight: NULL pointer");
+    EMER_REQUIRE(n_out >= 1 && n_out <= NARROW_MAX_OUT && k >= 1 && k <= NARROW_MAX_K, "emer_linear_narrow_bwd_weight: k=%d n_out=%d", k, n_out);
+    int64_t chunks = 148 * 8;
+    int64_t rows = ceil_div(n, chunks);
+    if (rows < 64) rows = 64;
+    chunks = ceil_div(n, rows);
+    narrow_wgrad_kernel<<<(unsigned)chunks, 256, 0, (cudaStream_t)stream>>>(x, ldx, dz, lddz, dw, db, n, k, n_out, rows);
+    return check_launch("emer_linear_narrow_bwd_weight");
+}

@@ -94,6 +94,16 @@ int emer_linear_bwd_weight(const float* x, int64_t ldx, const float* dy, int64_t
                            const float* y, int64_t ldy, int act, float* dw, float* db,
                            int64_t n, int k, int n_out, void* stream);
 
+/* Narrow heads (n_out <= 8, k <= 256: rgb 64->3, density 64->1, flow 64->6, shadow 64->1): streaming
+ * FFMA kernels; bwd_data fuses the ReLU mask of the layer below like the tensor-core kernel. */
+int emer_linear_narrow_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y,
+                           int64_t ldy, int64_t n, int k, int n_out, int act, void* stream);
+int emer_linear_narrow_bwd_data(const float* dz, int64_t lddz, const float* w, float* dx, int64_t lddx,
+                                const float* relu_src, int64_t ld_relu, int relu_cols, int64_t n, int k,
+                                int n_out, void* stream);
+int emer_linear_narrow_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
+                                  float* db, int64_t n, int k, int n_out, void* stream);
+
 /* Same contracts on the tcgen05 tensor cores: fp32 operands split into tf32 hi+lo, three
  * tcgen05.mma.kind::tf32 per k-step accumulate A_lo*B_hi + A_hi*B_lo + A_hi*B_hi in TMEM
  * (fp32-accurate "3xTF32"; see emernerf_b200/csrc/linear_tc.cu).  Widths: k, n_out <= 256. */
