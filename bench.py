@@ -300,9 +300,26 @@ def run_ours(args):
     # per kernel).  The ncu launch list under profiles/ must agree on the kernel's SHARE.
     table = kernel_table(tr, sync, steps=3)          # every rank runs it (the steps all-reduce)
 
+    if args.profile_all and rank == 0:
+        # all GPU kernels of one eager step (library + torch glue), by device time
+        from torch.profiler import ProfilerActivity, profile
+
+        tr._profiling = True
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            tr.step(0, False)
+            torch.cuda.synchronize()
+        tr._profiling = False
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:40]
+        tot = sum(e.device_time_total for e in prof.key_averages())
+        print(f"# --- all kernels of one eager step: {tot / 1e3:.3f} ms device time", file=sys.stderr)
+        for e in rows:
+            print(f"#   {e.device_time_total / 1e3:8.3f} ms n={e.count:4d}  {e.key[:110]}", file=sys.stderr)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        if world > 1:                     # leave together with rank 0 (see the end of this function)
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         return
 
     peaks = {}
@@ -358,8 +375,12 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, steps=2, warmup=1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: a plain destroy_process_group() was seen to hang at exit
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------- the CPU arm
