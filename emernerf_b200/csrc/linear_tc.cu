@@ -181,32 +181,51 @@ struct Params {
     long long* dbg;       // optional phase timers (cycles) of CTA 0 / thread 0; NULL in production
 };
 
-// a_stages in {1, 2} operand stages, raw_stages in {2, 4} cp.async stages (host picks the pair that
-// lets the most CTAs share an SM: the kernel is instruction-latency bound per CTA, co-resident
-// CTAs fill each other's bubbles).
+// Warp-specialised: 8 converter/epilogue warps (NT = 256 threads) + 1 MMA-issuing warp.
+//   converters : cp.async raw ring -> split hi/lo -> operand stage s -> arrive full[s]
+//                ... last chunk of a tile: wait accum -> epilogue -> arrive acc_free
+//   issuer     : wait full[s] -> 3 tcgen05.mma per k-step -> commit empty[s] (and accum on the last chunk)
+// so the ~100 cycles each tcgen05.mma costs its issuing thread (phase timers, profiles/) no longer sit
+// on the converters' critical path.  a_stages / raw_stages / ring_bytes are picked by the host so that
+// 2-3 CTAs share an SM whenever shared memory allows.
+constexpr int NT_ALL = NT + 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void conv_sync() {        // barrier among the 256 converter threads only
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
 template <bool BWD, int ACT>
-__global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
+__global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [B_hi | B_lo | A ring: a_stages x (hi, lo) | raw ring | bias | barriers]
+    // layout: [B_hi | B_lo | operand ring / epilogue staging | raw ring | bias | barriers]
     const int b_panel = p.n_pad * 16;
     const int b_bytes = (p.kred_pad / 4) * b_panel;
     uint8_t* b_hi = smem;
     uint8_t* b_lo = smem + b_bytes;
     uint8_t* a_ring = smem + 2 * b_bytes;
-    uint8_t* raw = a_ring + p.ring_bytes;               // ring area also serves as the epilogue staging tile
+    uint8_t* raw = a_ring + p.ring_bytes;
     float* bias_s = reinterpret_cast<float*>(raw + (p.use_async ? p.raw_stages * RAW_STAGE : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
-    uint64_t* empty_bar = bars;                  // [2]
-    uint64_t* accum_bar = bars + 2;              // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* full_bar = bars;                   // [2] converters -> issuer
+    uint64_t* empty_bar = bars + 2;              // [2] issuer (tcgen05.commit) -> converters
+    uint64_t* accum_bar = bars + 4;              // [1] issuer -> epilogue
+    uint64_t* accfree_bar = bars + 5;            // [1] epilogue -> issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const bool is_issuer = warp == NT / 32;
 
     if (tid == 0) {
+        mbar_init(&full_bar[0], NT);
+        mbar_init(&full_bar[1], NT);
         mbar_init(&empty_bar[0], 1);
         mbar_init(&empty_bar[1], 1);
         mbar_init(accum_bar, 1);
+        mbar_init(accfree_bar, NT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -219,14 +238,11 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
     const int total = my_tiles * n_chunks;
     const int a_stages = p.a_stages, raw_stages = p.raw_stages;
 
-    // cp.async producer: chunk (tile tl, k-chunk c) -> raw stage.  Thread t copies, for i in 0..3, the
-    // 16 bytes (row = i*32 + t/8, quad = t%8) into its own slot (i*NT + t): a row's 128 B are read
-    // by 8 consecutive threads (coalesced) and the slots of a warp are contiguous (conflict-free).
     constexpr int PIECES = ROWS * (CHUNK / 4) / NT;     // 4
-    const int my_r = tid >> 3, my_q = tid & 7;
-    const int64_t piece_stride = (int64_t)(NT / 8) * p.lda;          // 32 rows down
+    const int my_r = (tid & (NT - 1)) >> 3, my_q = tid & 7;
+    const int64_t piece_stride = (int64_t)(NT / 8) * p.lda;
     const float* thread_base = p.a + (int64_t)my_r * p.lda + my_q * 4;
-    int i_tl = 0, i_c = 0, i_stage = 0;                  // next chunk to issue (running counters: no division)
+    int i_tl = 0, i_c = 0, i_stage = 0;
     auto issue_next = [&]() {
         const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i_tl * gridDim.x) * ROWS;
         const bool kok = i_c * CHUNK + my_q * 4 < p.kred;
@@ -243,242 +259,239 @@ __global__ void __launch_bounds__(NT) tc_linear_kernel(const Params p) {
         if (++i_stage == raw_stages) i_stage = 0;
     };
     int issued = 0;
-    if (p.use_async) {
+    if (!is_issuer && p.use_async) {
         for (int g = 0; g < raw_stages - 1; ++g) {
             if (issued < total) { issue_next(); ++issued; }
             cp_async_commit();
         }
     }
 
-    // ---- resident B operand: hi/lo panels of W (fwd: B[n][r] = W[n, r]; bwd: B[n = k_in][r = o] = W[o, k_in])
-    if (!BWD) {
-        for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
-            const int nn = e / p.kred_pad, r = e - nn * p.kred_pad;       // consecutive threads: consecutive r
-            float v = 0.0f;
-            if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)nn * p.k + r);
-            float hi, lo;
-            split(v, hi, lo);
-            const int off = (r >> 2) * b_panel + nn * 16 + (r & 3) * 4;
-            *reinterpret_cast<float*>(b_hi + off) = hi;
-            *reinterpret_cast<float*>(b_lo + off) = lo;
+    // ---- resident B operand (converter threads): hi/lo panels of W
+    if (!is_issuer) {
+        if (!BWD) {
+            for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
+                const int nn = e / p.kred_pad, r = e - nn * p.kred_pad;
+                float v = 0.0f;
+                if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)nn * p.k + r);
+                float hi, lo;
+                split(v, hi, lo);
+                const int off = (r >> 2) * b_panel + nn * 16 + (r & 3) * 4;
+                *reinterpret_cast<float*>(b_hi + off) = hi;
+                *reinterpret_cast<float*>(b_lo + off) = lo;
+            }
+            for (int e = tid; e < 256; e += NT) bias_s[e] = (p.bias && e < p.ncols) ? __ldg(p.bias + e) : 0.0f;
+        } else {
+            for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
+                const int r = e / p.n_pad, nn = e - r * p.n_pad;
+                float v = 0.0f;
+                if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)r * p.k + nn);
+                float hi, lo;
+                split(v, hi, lo);
+                const int off = (r >> 2) * b_panel + nn * 16 + (r & 3) * 4;
+                *reinterpret_cast<float*>(b_hi + off) = hi;
+                *reinterpret_cast<float*>(b_lo + off) = lo;
+            }
         }
-        for (int e = tid; e < 256; e += NT) bias_s[e] = (p.bias && e < p.ncols) ? __ldg(p.bias + e) : 0.0f;
-    } else {
-        for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
-            const int r = e / p.n_pad, nn = e - r * p.n_pad;              // consecutive threads: consecutive k_in
-            float v = 0.0f;
-            if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)r * p.k + nn);
-            float hi, lo;
-            split(v, hi, lo);
-            const int off = (r >> 2) * b_panel + nn * 16 + (r & 3) * 4;
-            *reinterpret_cast<float*>(b_hi + off) = hi;
-            *reinterpret_cast<float*>(b_lo + off) = lo;
-        }
+        fence_async_proxy();
     }
-    fence_async_proxy();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t idesc = make_idesc(128, p.n_pad);
-    const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
-    const bool vec_m = p.relu_src && (p.ld_relu % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.relu_src) & 15) == 0);
-    // descriptor templates: only the 14-bit start-address field changes between MMAs
-    const uint64_t desc_a = make_desc(0, A_PANEL, 128);
-    const uint64_t desc_b = make_desc(0, b_panel, 128);
-    const uint32_t a_ring_addr = smem_u32(a_ring) >> 4;
-    const uint32_t b_hi_addr = smem_u32(b_hi) >> 4, b_lo_addr = smem_u32(b_lo) >> 4;
 
-    const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_prev = timing ? clock64() : 0;
-#define TC_TICK(slot)                      \
-    if (timing) {                          \
-        const long long t_now = clock64(); \
-        tm[slot] += t_now - t_prev;        \
-        t_prev = t_now;                    \
-    }
-    int tl = 0, c = 0, rstage = 0;
-    uint32_t use0 = 0, use1 = 0;                 // fills of operand stage 0 / 1
-    for (int g = 0; g < total; ++g) {
-        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * ROWS;
-        const int k0 = c * CHUNK;
-        const int s = (a_stages == 2) ? (g & 1) : 0;
-        uint8_t* a_hi = a_ring + (s * 2) * A_STAGE;
-        uint8_t* a_lo = a_hi + A_STAGE;
-        if (p.use_async) {
-            if (issued < total) { issue_next(); ++issued; }
-            cp_async_commit();
-            TC_TICK(0)
-            if (raw_stages == 4) cp_async_wait<3>();
-            else cp_async_wait<1>();                   // this thread's pieces of chunk g have landed
-        }
-        TC_TICK(1)
-        // the MMAs that last read operand stage s must have retired
-        {
+    if (is_issuer) {
+        // ================= MMA issuer warp (one lane issues; the warp stays converged) =================
+        const uint32_t idesc = make_idesc(128, p.n_pad);
+        const uint64_t desc_a = make_desc(0, A_PANEL, 128);
+        const uint64_t desc_b = make_desc(0, b_panel, 128);
+        const uint32_t a_ring_addr = smem_u32(a_ring) >> 4;
+        const uint32_t b_hi_addr = smem_u32(b_hi) >> 4, b_lo_addr = smem_u32(b_lo) >> 4;
+        const uint32_t d1 = tmem_base + (uint32_t)p.n_pad;
+        int tl = 0, c = 0;
+        uint32_t use0 = 0, use1 = 0;
+        for (int g = 0; g < total; ++g) {
+            const int s = (a_stages == 2) ? (g & 1) : 0;
             const uint32_t uses = s ? use1 : use0;
-            if (uses > 0) mbar_wait(&empty_bar[s], (uses - 1) & 1);
-        }
-        TC_TICK(2)
-        const uint8_t* rs = raw + rstage * RAW_STAGE + tid * 16;
-        const int kk = k0 + my_q * 4;
-        const bool tail = k0 + CHUNK > p.kred;              // only the last chunk has columns to mask
-#pragma unroll
-        for (int i = 0; i < PIECES; ++i) {
-            const int r = i * (NT / 8) + my_r;
-            float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (p.use_async) {
-                const float4 t = *reinterpret_cast<const float4*>(rs + i * NT * 16);
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                if (tail) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (kk + j >= p.kred) v[j] = 0.0f;
-                }
-            } else {
-                const int64_t row = row0 + r;
-                if (row < p.n) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (kk + j < p.kred) {
-                            float t = __ldg(p.a + row * p.lda + kk + j);
-                            if (BWD && p.act != EMER_ACT_NONE) t = act_bwd(t, __ldg(p.yact + row * p.ldy + kk + j), p.act);
-                            v[j] = t;
-                        }
-                    }
-                }
-            }
-            float4 h, l;
-            split(v[0], h.x, l.x); split(v[1], h.y, l.y); split(v[2], h.z, l.z); split(v[3], h.w, l.w);
-            *reinterpret_cast<float4*>(a_hi + my_q * A_PANEL + r * 16) = h;
-            *reinterpret_cast<float4*>(a_lo + my_q * A_PANEL + r * 16) = l;
-        }
-        TC_TICK(3)
-        fence_async_proxy();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        tc_fence_before();
-        __syncthreads();
-        TC_TICK(4)
-        if (tid == 0) {
+            mbar_wait(&full_bar[s], uses & 1);                       // operands of chunk g are in place
+            if (c == 0 && tl > 0) mbar_wait(accfree_bar, (tl - 1) & 1);   // previous tile's accumulators drained
             tc_fence_after();
-            const int ksteps = min(CHUNK, p.kred_pad - k0) / 8;
-            const uint32_t a_hi_addr = a_ring_addr + (uint32_t)((s * 2) * A_STAGE >> 4);
-            const uint32_t a_lo_addr = a_hi_addr + (uint32_t)(A_STAGE >> 4);
-            const uint32_t b_off = (uint32_t)((k0 >> 2) * b_panel) >> 4;
-            const uint32_t d1 = tmem_base + (uint32_t)p.n_pad;
+            if ((tid & 31) == 0) {
+                const int k0 = c * CHUNK;
+                const int ksteps = min(CHUNK, p.kred_pad - k0) / 8;
+                const uint32_t a_hi_addr = a_ring_addr + (uint32_t)((s * 2) * A_STAGE >> 4);
+                const uint32_t a_lo_addr = a_hi_addr + (uint32_t)(A_STAGE >> 4);
+                const uint32_t b_off = (uint32_t)((k0 >> 2) * b_panel) >> 4;
 #pragma unroll 4
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t ao = (uint32_t)(ks * 2 * A_PANEL) >> 4;
-                const uint32_t bo = b_off + ((uint32_t)(ks * 2 * b_panel) >> 4);
-                const uint64_t da_hi = desc_a | (uint64_t)(a_hi_addr + ao);
-                const uint64_t da_lo = desc_a | (uint64_t)(a_lo_addr + ao);
-                const uint64_t db_hi = desc_b | (uint64_t)(b_hi_addr + bo);
-                const uint64_t db_lo = desc_b | (uint64_t)(b_lo_addr + bo);
-                const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
-                mma_tf32(tmem_base, da_hi, db_hi, idesc, first);      // chain 0
-                mma_tf32(d1, da_lo, db_hi, idesc, first);             // chain 1
-                mma_tf32(d1, da_hi, db_lo, idesc, 1u);
-            }
-            tc_commit(&empty_bar[s]);                        // operand stage reusable once these retire
-            if (c == n_chunks - 1) tc_commit(accum_bar);     // ... and the tile's accumulators are complete
-        }
-        if (s) ++use1; else ++use0;
-        if (++rstage == raw_stages) rstage = 0;
-        TC_TICK(5)
-        const bool last_chunk = (c == n_chunks - 1);
-        const int tile_idx = tl;
-        if (++c == n_chunks) { c = 0; ++tl; }
-        if (!last_chunk) continue;
-
-        // ---- epilogue: TMEM -> registers -> (bias, activation) -> shared staging -> coalesced global.
-        // All MMAs of the tile have retired, so the operand ring doubles as the staging buffer.
-        mbar_wait(accum_bar, tile_idx & 1);
-        tc_fence_after();
-        TC_TICK(6)
-        float* stage = reinterpret_cast<float*>(a_ring);
-        constexpr int SLD = 64 + 4;                          // staging row stride (floats): conflict-free
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const int my_row = tid & 127;
-        for (int cb = 0; cb < p.n_pad; cb += 64) {           // 64-column blocks
-            const int cw = min(64, p.n_pad - cb);
-            // warps w and w+4 share lane quadrant w: they take alternate 16-column groups
-            for (int c0 = (warp >> 2) * 16; c0 < cw; c0 += 32) {
-                uint32_t r0[16], r1[16];
-                tmem_ld16(lane_addr + (uint32_t)(cb + c0), r0);
-                tmem_ld16(lane_addr + (uint32_t)(p.n_pad + cb + c0), r1);
-                tmem_ld_wait();
-                float* dstp = stage + my_row * SLD + c0;
-#pragma unroll
-                for (int j0 = 0; j0 < 16; j0 += 4) {
-                    float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v = __uint_as_float(r0[j0 + j]) + __uint_as_float(r1[j0 + j]);
-                        if (!BWD) {
-                            v += bias_s[cb + c0 + j0 + j];
-                            if (ACT == EMER_ACT_RELU) v = v > 0.0f ? v : 0.0f;
-                            if (ACT == EMER_ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
-                        }
-                        o[j] = v;
-                    }
-                    *reinterpret_cast<float4*>(dstp + j0) = make_float4(o[0], o[1], o[2], o[3]);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t ao = (uint32_t)(ks * 2 * A_PANEL) >> 4;
+                    const uint32_t bo = b_off + ((uint32_t)(ks * 2 * b_panel) >> 4);
+                    const uint64_t da_hi = desc_a | (uint64_t)(a_hi_addr + ao);
+                    const uint64_t da_lo = desc_a | (uint64_t)(a_lo_addr + ao);
+                    const uint64_t db_hi = desc_b | (uint64_t)(b_hi_addr + bo);
+                    const uint64_t db_lo = desc_b | (uint64_t)(b_lo_addr + bo);
+                    const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
+                    mma_tf32(tmem_base, da_hi, db_hi, idesc, first);      // chain 0
+                    mma_tf32(d1, da_lo, db_hi, idesc, first);             // chain 1
+                    mma_tf32(d1, da_hi, db_lo, idesc, 1u);
                 }
+                tc_commit(&empty_bar[s]);
+                if (c == n_chunks - 1) tc_commit(accum_bar);
             }
-            __syncthreads();
-            // copy-out: consecutive threads write consecutive 16-byte pieces of a row
-            const int q_per_row = cw / 4;
-            for (int e = tid; e < ROWS * q_per_row; e += NT) {
-                const int r = e / q_per_row, q = e - r * q_per_row;
-                const int64_t row = row0 + r;
-                const int col = cb + q * 4;
-                if (row >= p.n || col >= p.ncols) continue;
-                float4 v = *reinterpret_cast<const float4*>(stage + r * SLD + q * 4);
-                float o[4] = {v.x, v.y, v.z, v.w};
-                const bool full = col + 3 < p.ncols;
-                if (BWD && p.relu_src && col < p.relu_cols) {
-                    const float* m = p.relu_src + row * p.ld_relu + col;
-                    if (vec_m && full && col + 3 < p.relu_cols) {
-                        const float4 mm = __ldg(reinterpret_cast<const float4*>(m));
-                        if (!(mm.x > 0.0f)) o[0] = 0.0f;
-                        if (!(mm.y > 0.0f)) o[1] = 0.0f;
-                        if (!(mm.z > 0.0f)) o[2] = 0.0f;
-                        if (!(mm.w > 0.0f)) o[3] = 0.0f;
-                    } else {
+            __syncwarp();
+            if (s) ++use1; else ++use0;
+            if (++c == n_chunks) { c = 0; ++tl; }
+        }
+    } else {
+        // ================= converter / epilogue warps =================
+        const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+        const bool vec_m = p.relu_src && (p.ld_relu % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.relu_src) & 15) == 0);
+        int tl = 0, c = 0, rstage = 0;
+        uint32_t use0 = 0, use1 = 0;
+        for (int g = 0; g < total; ++g) {
+            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)tl * gridDim.x) * ROWS;
+            const int k0 = c * CHUNK;
+            const int s = (a_stages == 2) ? (g & 1) : 0;
+            uint8_t* a_hi = a_ring + (s * 2) * A_STAGE;
+            uint8_t* a_lo = a_hi + A_STAGE;
+            if (p.use_async) {
+                if (issued < total) { issue_next(); ++issued; }
+                cp_async_commit();
+                if (raw_stages == 4) cp_async_wait<3>();
+                else cp_async_wait<1>();
+            }
+            {
+                const uint32_t uses = s ? use1 : use0;
+                if (uses > 0) mbar_wait(&empty_bar[s], (uses - 1) & 1);     // MMAs that read stage s retired
+            }
+            const uint8_t* rs = raw + rstage * RAW_STAGE + tid * 16;
+            const int kk = k0 + my_q * 4;
+            const bool tail = k0 + CHUNK > p.kred;
+#pragma unroll
+            for (int i = 0; i < PIECES; ++i) {
+                const int r = i * (NT / 8) + my_r;
+                float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (p.use_async) {
+                    const float4 t = *reinterpret_cast<const float4*>(rs + i * NT * 16);
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                    if (tail) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (col + j < p.ncols && col + j < p.relu_cols && !(__ldg(m + j) > 0.0f)) o[j] = 0.0f;
+                            if (kk + j >= p.kred) v[j] = 0.0f;
                     }
-                }
-                float* out = p.c + row * p.ldc + col;
-                if (vec_c && full) {
-                    if (BWD && p.accumulate) {
-                        const float4 old = *reinterpret_cast<const float4*>(out);
-                        o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
-                    }
-                    *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
                 } else {
+                    const int64_t row = row0 + r;
+                    if (row < p.n) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (col + j < p.ncols) {
-                            if (BWD && p.accumulate) o[j] += out[j];
-                            out[j] = o[j];
+                        for (int j = 0; j < 4; ++j) {
+                            if (kk + j < p.kred) {
+                                float t = __ldg(p.a + row * p.lda + kk + j);
+                                if (BWD && p.act != EMER_ACT_NONE) t = act_bwd(t, __ldg(p.yact + row * p.ldy + kk + j), p.act);
+                                v[j] = t;
+                            }
                         }
                     }
                 }
+                float4 h, l;
+                split(v[0], h.x, l.x); split(v[1], h.y, l.y); split(v[2], h.z, l.z); split(v[3], h.w, l.w);
+                *reinterpret_cast<float4*>(a_hi + my_q * A_PANEL + r * 16) = h;
+                *reinterpret_cast<float4*>(a_lo + my_q * A_PANEL + r * 16) = l;
             }
-            __syncthreads();         // staging buffer free (next block / next tile's operands)
-        }
-        tc_fence_before();           // TMEM reads done before the next tile's first MMA overwrites the accumulators
-        __syncthreads();
-        TC_TICK(7)
-    }
-#undef TC_TICK
-    if (timing) {
+            fence_async_proxy();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full_bar[s]);
+            if (s) ++use1; else ++use0;
+            if (++rstage == raw_stages) rstage = 0;
+            const bool last_chunk = (c == n_chunks - 1);
+            const int tile_idx = tl;
+            if (++c == n_chunks) { c = 0; ++tl; }
+            if (!last_chunk) continue;
+
+            // ---- epilogue: TMEM -> registers -> (bias, activation) -> shared staging -> coalesced global.
+            // All MMAs of the tile have retired (accum barrier), so the operand ring doubles as staging.
+            mbar_wait(accum_bar, tile_idx & 1);
+            tc_fence_after();
+            float* stage = reinterpret_cast<float*>(a_ring);
+            constexpr int SLD = 64 + 4;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            const int my_row = tid & 127;
+            for (int cb = 0; cb < p.n_pad; cb += 64) {
+                const int cw = min(64, p.n_pad - cb);
+                for (int c0 = (warp >> 2) * 16; c0 < cw; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(lane_addr + (uint32_t)(cb + c0), r0);
+                    tmem_ld16(lane_addr + (uint32_t)(p.n_pad + cb + c0), r1);
+                    tmem_ld_wait();
+                    float* dstp = stage + my_row * SLD + c0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) p.dbg[i] = tm[i];
-        p.dbg[8] = total;
-        p.dbg[9] = my_tiles;
+                    for (int j0 = 0; j0 < 16; j0 += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v = __uint_as_float(r0[j0 + j]) + __uint_as_float(r1[j0 + j]);
+                            if (!BWD) {
+                                v += bias_s[cb + c0 + j0 + j];
+                                if (ACT == EMER_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+                                if (ACT == EMER_ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+                            }
+                            o[j] = v;
+                        }
+                        *reinterpret_cast<float4*>(dstp + j0) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                if (cb + 64 >= p.n_pad) {
+                    // last TMEM read of this tile done: let the issuer start the next tile's MMAs
+                    tc_fence_before();
+                    mbar_arrive(accfree_bar);
+                }
+                conv_sync();
+                // copy-out: consecutive threads write consecutive 16-byte pieces of a row
+                const int q_per_row = cw / 4;                  // 4, 8, 12 or 16
+                const int rows_per_pass = NT / q_per_row;      // exact for 4, 8, 16; 12 -> 21 rows (+4 idle threads)
+                const int q = tid % q_per_row, r_first = tid / q_per_row;
+                if (r_first < rows_per_pass) {
+                    for (int r = r_first; r < ROWS; r += rows_per_pass) {
+                        const int64_t row = row0 + r;
+                        const int col = cb + q * 4;
+                        if (row >= p.n || col >= p.ncols) continue;
+                        const float4 sv = *reinterpret_cast<const float4*>(stage + r * SLD + q * 4);
+                        float o[4] = {sv.x, sv.y, sv.z, sv.w};
+                        const bool full = col + 3 < p.ncols;
+                        if (BWD && p.relu_src && col < p.relu_cols) {
+                            const float* m = p.relu_src + row * p.ld_relu + col;
+                            if (vec_m && full && col + 3 < p.relu_cols) {
+                                const float4 mm = __ldg(reinterpret_cast<const float4*>(m));
+                                if (!(mm.x > 0.0f)) o[0] = 0.0f;
+                                if (!(mm.y > 0.0f)) o[1] = 0.0f;
+                                if (!(mm.z > 0.0f)) o[2] = 0.0f;
+                                if (!(mm.w > 0.0f)) o[3] = 0.0f;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (col + j < p.ncols && col + j < p.relu_cols && !(__ldg(m + j) > 0.0f)) o[j] = 0.0f;
+                            }
+                        }
+                        float* out = p.c + row * p.ldc + col;
+                        if (vec_c && full) {
+                            if (BWD && p.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(out);
+                                o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+                            }
+                            *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (col + j < p.ncols) {
+                                    if (BWD && p.accumulate) o[j] += out[j];
+                                    out[j] = o[j];
+                                }
+                            }
+                        }
+                    }
+                }
+                conv_sync();         // staging buffer free (next column block / next tile's operands)
+            }
+        }
+        if (p.use_async) cp_async_wait<0>();
     }
-    if (p.use_async) cp_async_wait<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -498,7 +511,7 @@ static int launch_t(Params& p, size_t smem, int64_t grid, cudaStream_t st, const
         }
         configured = smem;
     }
-    tc_linear_kernel<BWD, ACT><<<(unsigned)grid, NT, smem, st>>>(p);
+    tc_linear_kernel<BWD, ACT><<<(unsigned)grid, NT_ALL, smem, st>>>(p);
     return check_launch(what);
 }
 
@@ -513,7 +526,7 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.n_pad) p.tmem_cols *= 2;
     const size_t w_bytes = (size_t)2 * (p.kred_pad / 4) * p.n_pad * 16;
-    const size_t misc = 256 * 4 + 3 * 8 + 16;
+    const size_t misc = 256 * 4 + 6 * 8 + 16;
     const size_t staging = (size_t)ROWS * 68 * 4;                        // epilogue tile: 128 x (64+4) floats
     const size_t ring1 = staging > (size_t)2 * A_STAGE ? staging : (size_t)2 * A_STAGE;
     const size_t ring2 = (size_t)2 * 2 * A_STAGE;
