@@ -300,6 +300,17 @@ def run_ours(args):
     # per kernel).  The ncu launch list under profiles/ must agree on the kernel's SHARE.
     table = kernel_table(tr, sync, steps=3)          # every rank runs it (the steps all-reduce)
 
+    if args.profile_all and tr.use_graph and hasattr(tr, "graphs"):
+        for prg in (False, True):               # device time of each captured branch of the step
+            sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                tr.graphs[prg].replay()
+            e1.record()
+            sync()
+            if rank == 0:
+                print(f"# graph replay, proposal update = {prg}: {e0.elapsed_time(e1) / 5:.3f} ms", file=sys.stderr)
     if args.profile_all and rank == 0:
         # all GPU kernels of one eager step (library + torch glue), by device time
         from torch.profiler import ProfilerActivity, profile

@@ -132,3 +132,33 @@ def test_ops_refuse_cpu_tensors():
         _ops.grid_encode(torch.rand(4, 3), torch.zeros(g.n_params), g)
     with pytest.raises(RuntimeError, match="CUDA"):
         _ops.linear(torch.rand(4, 8), torch.rand(3, 8), None)
+
+
+def test_sorted_interp_quad_searchsorted_equals_dense_mask():
+    """The searchsorted formulation of the zip-nerf interpolation equals the reference's dense-mask
+    formulation (and the oracle's restatement of it) on blurred step functions, values and gradients."""
+    from emernerf_b200.third_party import nerfacc_prop_net as pn
+
+    g = torch.Generator().manual_seed(0)
+    R = 40
+    s = torch.sort(torch.rand(R, 65, generator=g), -1).values
+    w = torch.rand(R, 64, generator=g)
+    w[:, ::7] = 0.0
+    for r in (0.03, 0.003):
+        c, wv = pn.blur_stepfun(s, w, r)
+        area = 0.5 * (wv[..., 1:] + wv[..., :-1]) * (c[..., 1:] - c[..., :-1])
+        cdf = torch.cat([torch.zeros_like(area[..., :1]), torch.cumsum(area, -1)], -1)
+        for n in (129, 65):
+            # queries inside the knot range, as in compute_loss (proposal edges lie in [0, 1], the blurred
+            # knots span [min - r, max + r]); beyond the last knot the reference's masked arg-max picks an
+            # arbitrary tied index and the two forms may differ by an ulp
+            x = torch.sort(torch.rand(R, n, generator=g), -1).values
+            x = (x * (s[:, -1:] - s[:, :1]) + s[:, :1]).requires_grad_(True)
+            a = pn.sorted_interp_quad(x, c, wv, cdf)
+            b = pn.sorted_interp_quad_dense(x, c, wv, cdf)
+            d = hotpath.sorted_interp_quad(x, c, wv, cdf)
+            assert torch.equal(b, d)
+            assert torch.allclose(a, b, rtol=0, atol=1e-7)
+            ga, = torch.autograd.grad(a.sum(), x)
+            gb, = torch.autograd.grad(b.sum(), x)
+            assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-6)   # (unused by the loss: its inputs are detached)
