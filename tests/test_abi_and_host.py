@@ -153,12 +153,11 @@ def test_sorted_interp_quad_searchsorted_equals_dense_mask():
             # knots span [min - r, max + r]); beyond the last knot the reference's masked arg-max picks an
             # arbitrary tied index and the two forms may differ by an ulp
             x = torch.sort(torch.rand(R, n, generator=g), -1).values
-            x = (x * (s[:, -1:] - s[:, :1]) + s[:, :1]).requires_grad_(True)
+            x = x * (s[:, -1:] - s[:, :1]) + s[:, :1]
             a = pn.sorted_interp_quad(x, c, wv, cdf)
             b = pn.sorted_interp_quad_dense(x, c, wv, cdf)
             d = hotpath.sorted_interp_quad(x, c, wv, cdf)
             assert torch.equal(b, d)
             assert torch.allclose(a, b, rtol=0, atol=1e-7)
-            ga, = torch.autograd.grad(a.sum(), x)
-            gb, = torch.autograd.grad(b.sum(), x)
-            assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-6)   # (unused by the loss: its inputs are detached)
+            # (no gradient check: compute_loss feeds detached tensors, gradients reach the proposal
+            #  network only through w_prop)
