@@ -588,9 +588,6 @@ namespace tcw {
 
 using namespace emer::tc;
 
-constexpr int WROWS = 64;                     // rows per tile = 16 row-quads = 8 tf32 k-steps
-constexpr int RQ = WROWS / 4;
-
 struct WParams {
     const float* x;
     int64_t ldx;
@@ -603,31 +600,41 @@ struct WParams {
     int k_pad4;          // k rounded to 4  (raw row width)
     int n_pad;           // n_out rounded to 16
     int m_blocks;        // ceil(k / 128)
-    int raw_stages;      // 1 or 2
+    int w_rows;          // rows per tile: 64 or 32 (4 rows = one 16-byte k group, 8 rows = one k-step)
+    int a_rows;          // feature rows per A panel: 64 when k <= 64 (the MMA's rows 64..127 then read the next
+                         // panel's finite data and land in accumulator lanes nobody reads), else 128
+    int nbuf;            // operand buffers (2: conversion of tile t+1 overlaps the MMAs of tile t)
+    int raw_stages;      // cp.async stages of raw rows
     int tmem_cols;
 };
 
-__global__ void __launch_bounds__(NT) tc_wgrad_kernel(const WParams p) {
+// 8 converter warps + 1 MMA-issuing warp, mbarrier ring between them (see tc_linear_kernel).
+__global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int a_panel = 128 * 16 + 16;                     // 2064
+    const int RQn = p.w_rows / 4;
+    const int a_panel = p.a_rows * 16 + 16;
     const int b_panel = p.n_pad * 16 + 16;
-    const int a_bytes = p.m_blocks * RQ * a_panel;         // one of hi / lo
-    const int b_bytes = RQ * b_panel;
-    const int rawx_bytes = WROWS * p.k_pad4 * 4;
-    const int rawz_bytes = WROWS * p.n_pad * 4;
-    uint8_t* a_hi = smem;
-    uint8_t* a_lo = a_hi + a_bytes;
-    uint8_t* b_hi = a_lo + a_bytes;
-    uint8_t* b_lo = b_hi + b_bytes;
-    uint8_t* raw = b_lo + b_bytes;                          // raw_stages x (X rows | dZ rows)
+    const int a_bytes = p.m_blocks * RQn * a_panel;         // one of hi / lo, one buffer
+    const int b_bytes = RQn * b_panel;
+    const int buf_bytes = 2 * a_bytes + 2 * b_bytes;        // [A_hi | A_lo | B_hi | B_lo]
+    const int rawx_bytes = p.w_rows * p.k_pad4 * 4;
+    const int rawz_bytes = p.w_rows * p.n_pad * 4;
     const int raw_stage = rawx_bytes + rawz_bytes;
-    uint64_t* done_bar = reinterpret_cast<uint64_t*>(raw + p.raw_stages * raw_stage);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+    uint8_t* ops = smem;
+    uint8_t* raw = ops + p.nbuf * buf_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw + p.raw_stages * raw_stage);
+    uint64_t* full_bar = bars;            // [2]
+    uint64_t* empty_bar = bars + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const bool is_issuer = warp == NT / 32;
     if (tid == 0) {
-        mbar_init(done_bar, 1);
+        mbar_init(&full_bar[0], NT);
+        mbar_init(&full_bar[1], NT);
+        mbar_init(&empty_bar[0], 1);
+        mbar_init(&empty_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -635,141 +642,162 @@ __global__ void __launch_bounds__(NT) tc_wgrad_kernel(const WParams p) {
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     }
     // operand buffers start as zeros: padding features / columns never hold NaN bit patterns
-    for (int i = tid * 16; i < 2 * a_bytes + 2 * b_bytes; i += NT * 16)
+    for (int i = tid * 16; i < p.nbuf * buf_bytes; i += NT_ALL * 16)
         *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    const int64_t n_tiles = (p.n + WROWS - 1) / WROWS;
+    const int64_t n_tiles = (p.n + p.w_rows - 1) / p.w_rows;
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int xq = p.k_pad4 / 4, zq = p.n_pad / 4;
 
-    auto issue = [&](int t) {
-        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * WROWS;
+    auto issue = [&](int t) {             // converter threads only
+        const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * p.w_rows;
         uint8_t* dx = raw + (t % p.raw_stages) * raw_stage;
         uint8_t* dzs = dx + rawx_bytes;
-        for (int e = tid; e < WROWS * xq; e += NT) {
+        for (int e = tid; e < p.w_rows * xq; e += NT) {
             const int r = e / xq, q = e - r * xq;
             const int64_t row = row0 + r;
             const bool ok = (row < p.n) && (q * 4 < p.k);
             cp_async16(dx + e * 16, ok ? (p.x + row * p.ldx + q * 4) : p.x, ok ? 16u : 0u);
         }
-        for (int e = tid; e < WROWS * zq; e += NT) {
+        for (int e = tid; e < p.w_rows * zq; e += NT) {
             const int r = e / zq, q = e - r * zq;
             const int64_t row = row0 + r;
             const bool ok = (row < p.n) && (q * 4 < p.n_out);
             cp_async16(dzs + e * 16, ok ? (p.dz + row * p.lddz + q * 4) : p.dz, ok ? 16u : 0u);
         }
     };
-    for (int t = 0; t < p.raw_stages; ++t) {
-        if (t < my_tiles) issue(t);
-        cp_async_commit();
+    if (!is_issuer) {
+        for (int t = 0; t < p.raw_stages; ++t) {
+            if (t < my_tiles) issue(t);
+            cp_async_commit();
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t idesc = make_idesc(128, p.n_pad);
-    float bsum = 0.0f;        // thread t < n_out owns db[t]
 
-    for (int t = 0; t < my_tiles; ++t) {
-        // raw tile t landed?  (each thread waits for its own pieces, the barrier below publishes all)
-        if (p.raw_stages == 2) cp_async_wait<1>();
-        else cp_async_wait<0>();
-        __syncthreads();
-        // the previous tile's MMAs must have finished reading the operand buffers
-        if (t > 0) mbar_wait(done_bar, (t - 1) & 1);
-        const float* rx = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage);
-        const float* rz = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage + rawx_bytes);
-        // ---- A = X^T: item (rq, f): rows 4rq..4rq+3 of feature f -> one 16-byte k group
-        for (int e = tid; e < RQ * p.k_pad4; e += NT) {
-            const int rq = e / p.k_pad4, f = e - rq * p.k_pad4;
-            float4 h, l;
-            if (f < p.k) {
-                const float* src = rx + (rq * 4) * p.k_pad4 + f;
-                split(src[0], h.x, l.x);
-                split(src[p.k_pad4], h.y, l.y);
-                split(src[2 * p.k_pad4], h.z, l.z);
-                split(src[3 * p.k_pad4], h.w, l.w);
-            } else {
-                h = l = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const int off = ((f >> 7) * RQ + rq) * a_panel + (f & 127) * 16;
-            *reinterpret_cast<float4*>(a_hi + off) = h;
-            *reinterpret_cast<float4*>(a_lo + off) = l;
-        }
-        // ---- B = dZ^T
-        for (int e = tid; e < RQ * p.n_pad; e += NT) {
-            const int rq = e / p.n_pad, o = e - rq * p.n_pad;
-            float4 h, l;
-            if (o < p.n_out) {
-                const float* src = rz + (rq * 4) * p.n_pad + o;
-                split(src[0], h.x, l.x);
-                split(src[p.n_pad], h.y, l.y);
-                split(src[2 * p.n_pad], h.z, l.z);
-                split(src[3 * p.n_pad], h.w, l.w);
-            } else {
-                h = l = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            *reinterpret_cast<float4*>(b_hi + rq * b_panel + o * 16) = h;
-            *reinterpret_cast<float4*>(b_lo + rq * b_panel + o * 16) = l;
-        }
-        if (p.db && tid < p.n_out) {
-#pragma unroll 8
-            for (int r = 0; r < WROWS; ++r) bsum += rz[r * p.n_pad + tid];
-        }
-        fence_async_proxy();
-        tc_fence_before();
-        __syncthreads();                    // operands complete; raw stage t free again
-        if (t + p.raw_stages < my_tiles) issue(t + p.raw_stages);
-        cp_async_commit();
-        if (tid == 0) {
+    if (is_issuer) {
+        const uint32_t idesc = make_idesc(128, p.n_pad);
+        const uint64_t desc_a = make_desc(0, a_panel, 128), desc_b = make_desc(0, b_panel, 128);
+        const int ksteps = p.w_rows / 8;
+        uint32_t use[2] = {0, 0};
+        for (int t = 0; t < my_tiles; ++t) {
+            const int b = (p.nbuf == 2) ? (t & 1) : 0;
+            mbar_wait(&full_bar[b], use[b] & 1);
             tc_fence_after();
-            const uint64_t desc_a = make_desc(0, a_panel, 128), desc_b = make_desc(0, b_panel, 128);
-            const uint32_t a_hi_addr = smem_u32(a_hi) >> 4, a_lo_addr = smem_u32(a_lo) >> 4;
-            const uint32_t b_hi_addr = smem_u32(b_hi) >> 4, b_lo_addr = smem_u32(b_lo) >> 4;
-#pragma unroll
-            for (int ks = 0; ks < WROWS / 8; ++ks) {
-                const uint32_t bo = (uint32_t)(ks * 2 * b_panel) >> 4;
-                const uint64_t db_hi = desc_b | (uint64_t)(b_hi_addr + bo);
-                const uint64_t db_lo = desc_b | (uint64_t)(b_lo_addr + bo);
-                const uint32_t acc = (t == 0 && ks == 0) ? 0u : 1u;
-                for (int mb = 0; mb < p.m_blocks; ++mb) {
-                    const uint32_t ao = (uint32_t)((mb * RQ + ks * 2) * a_panel) >> 4;
-                    const uint64_t da_hi = desc_a | (uint64_t)(a_hi_addr + ao);
-                    const uint64_t da_lo = desc_a | (uint64_t)(a_lo_addr + ao);
-                    const uint32_t d0 = tmem_base + (uint32_t)(mb * 2 * p.n_pad);
-                    mma_tf32(d0, da_hi, db_hi, idesc, acc);                           // chain 0
-                    mma_tf32(d0 + (uint32_t)p.n_pad, da_lo, db_hi, idesc, acc);       // chain 1
-                    mma_tf32(d0 + (uint32_t)p.n_pad, da_hi, db_lo, idesc, 1u);
+            if ((tid & 31) == 0) {
+                const uint32_t base = smem_u32(ops + b * buf_bytes);
+                const uint32_t a_hi_addr = base >> 4, a_lo_addr = (base + a_bytes) >> 4;
+                const uint32_t b_hi_addr = (base + 2 * a_bytes) >> 4, b_lo_addr = (base + 2 * a_bytes + b_bytes) >> 4;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t bo = (uint32_t)(ks * 2 * b_panel) >> 4;
+                    const uint64_t db_hi = desc_b | (uint64_t)(b_hi_addr + bo);
+                    const uint64_t db_lo = desc_b | (uint64_t)(b_lo_addr + bo);
+                    const uint32_t acc = (t == 0 && ks == 0) ? 0u : 1u;
+                    for (int mb = 0; mb < p.m_blocks; ++mb) {
+                        const uint32_t ao = (uint32_t)((mb * RQn + ks * 2) * a_panel) >> 4;
+                        const uint64_t da_hi = desc_a | (uint64_t)(a_hi_addr + ao);
+                        const uint64_t da_lo = desc_a | (uint64_t)(a_lo_addr + ao);
+                        const uint32_t d0 = tmem_base + (uint32_t)(mb * 2 * p.n_pad);
+                        mma_tf32(d0, da_hi, db_hi, idesc, acc);                           // chain 0
+                        mma_tf32(d0 + (uint32_t)p.n_pad, da_lo, db_hi, idesc, acc);       // chain 1
+                        mma_tf32(d0 + (uint32_t)p.n_pad, da_hi, db_lo, idesc, 1u);
+                    }
                 }
+                tc_commit(&empty_bar[b]);
             }
-            tc_commit(done_bar);
+            __syncwarp();
+            ++use[b];
         }
-    }
-    if (my_tiles > 0) {
-        mbar_wait(done_bar, (my_tiles - 1) & 1);
-        tc_fence_after();
-        // flush: lane f of block mb holds dW^T[mb*128 + f, :]
-        for (int mb = 0; mb < p.m_blocks; ++mb) {
-            const int f = mb * 128 + (tid & 127);
-            const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * 2 * p.n_pad);
-            for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
-                uint32_t r0[16], r1[16];
-                tmem_ld16(lane_addr + (uint32_t)c0, r0);
-                tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
-                tmem_ld_wait();
+    } else {
+        float bsum = 0.0f;        // thread t < n_out owns db[t]
+        uint32_t use[2] = {0, 0};
+        for (int t = 0; t < my_tiles; ++t) {
+            const int b = (p.nbuf == 2) ? (t & 1) : 0;
+            // raw tile t landed (each thread waits for its own pieces; the barrier publishes all of them)
+            if (p.raw_stages == 2) cp_async_wait<1>();
+            else cp_async_wait<0>();
+            conv_sync();
+            if (use[b] > 0) mbar_wait(&empty_bar[b], (use[b] - 1) & 1);     // MMAs that read buffer b retired
+            uint8_t* a_hi = ops + b * buf_bytes;
+            uint8_t* a_lo = a_hi + a_bytes;
+            uint8_t* b_hi = a_lo + a_bytes;
+            uint8_t* b_lo = b_hi + b_bytes;
+            const float* rx = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage);
+            const float* rz = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage + rawx_bytes);
+            // ---- A = X^T: item (rq, f): rows 4rq..4rq+3 of feature f -> one 16-byte k group
+            for (int e = tid; e < RQn * p.k_pad4; e += NT) {
+                const int rq = e / p.k_pad4, f = e - rq * p.k_pad4;
+                float4 h, l;
                 if (f < p.k) {
+                    const float* src = rx + (rq * 4) * p.k_pad4 + f;
+                    split(src[0], h.x, l.x);
+                    split(src[p.k_pad4], h.y, l.y);
+                    split(src[2 * p.k_pad4], h.z, l.z);
+                    split(src[3 * p.k_pad4], h.w, l.w);
+                } else {
+                    h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const int off = (p.a_rows == 128) ? ((f >> 7) * RQn + rq) * a_panel + (f & 127) * 16
+                                                  : rq * a_panel + f * 16;
+                *reinterpret_cast<float4*>(a_hi + off) = h;
+                *reinterpret_cast<float4*>(a_lo + off) = l;
+            }
+            // ---- B = dZ^T
+            for (int e = tid; e < RQn * p.n_pad; e += NT) {
+                const int rq = e / p.n_pad, o = e - rq * p.n_pad;
+                float4 h, l;
+                if (o < p.n_out) {
+                    const float* src = rz + (rq * 4) * p.n_pad + o;
+                    split(src[0], h.x, l.x);
+                    split(src[p.n_pad], h.y, l.y);
+                    split(src[2 * p.n_pad], h.z, l.z);
+                    split(src[3 * p.n_pad], h.w, l.w);
+                } else {
+                    h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                *reinterpret_cast<float4*>(b_hi + rq * b_panel + o * 16) = h;
+                *reinterpret_cast<float4*>(b_lo + rq * b_panel + o * 16) = l;
+            }
+            if (p.db && tid < p.n_out) {
+                for (int r = 0; r < p.w_rows; ++r) bsum += rz[r * p.n_pad + tid];
+            }
+            fence_async_proxy();
+            mbar_arrive(&full_bar[b]);
+            ++use[b];
+            conv_sync();                        // everyone is done reading raw stage t
+            if (t + p.raw_stages < my_tiles) issue(t + p.raw_stages);
+            cp_async_commit();
+        }
+        if (my_tiles > 0) {
+            const int lb = (p.nbuf == 2) ? ((my_tiles - 1) & 1) : 0;
+            mbar_wait(&empty_bar[lb], (use[lb] - 1) & 1);          // the last tile's MMAs retired
+            if (p.nbuf == 2 && my_tiles > 1) mbar_wait(&empty_bar[lb ^ 1], (use[lb ^ 1] - 1) & 1);
+            tc_fence_after();
+            // flush: lane f of block mb holds dW^T[mb*128 + f, :]
+            for (int mb = 0; mb < p.m_blocks; ++mb) {
+                const int f = mb * 128 + (tid & 127);
+                const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * 2 * p.n_pad);
+                for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(lane_addr + (uint32_t)c0, r0);
+                    tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
+                    tmem_ld_wait();
+                    if (f < p.k) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int o = c0 + j;
-                        if (o < p.n_out)
-                            atomicAdd(p.dw + (int64_t)o * p.k + f, __uint_as_float(r0[j]) + __uint_as_float(r1[j]));
+                        for (int j = 0; j < 16; ++j) {
+                            const int o = c0 + j;
+                            if (o < p.n_out)
+                                atomicAdd(p.dw + (int64_t)o * p.k + f, __uint_as_float(r0[j]) + __uint_as_float(r1[j]));
+                        }
                     }
                 }
             }
+            if (p.db && tid < p.n_out) atomicAdd(p.db + tid, bsum);
         }
-        if (p.db && tid < p.n_out) atomicAdd(p.db + tid, bsum);
+        cp_async_wait<0>();
     }
-    cp_async_wait<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -833,11 +861,22 @@ extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const floa
     p.tmem_cols = 32;
     while (p.tmem_cols < p.m_blocks * 2 * p.n_pad) p.tmem_cols *= 2;
     EMER_REQUIRE(p.tmem_cols <= 512, "emer_linear_tc_bwd_weight: accumulator does not fit TMEM");
-    const size_t ops = (size_t)2 * p.m_blocks * RQ * (128 * 16 + 16) + (size_t)2 * RQ * (p.n_pad * 16 + 16);
-    const size_t raw_stage = (size_t)WROWS * (p.k_pad4 + p.n_pad) * 4;
-    p.raw_stages = (ops + 2 * raw_stage + 64 <= 227 * 1024) ? 2 : 1;
-    const size_t smem = ops + p.raw_stages * raw_stage + 8 + 16;
-    EMER_REQUIRE(smem <= 227 * 1024, "emer_linear_tc_bwd_weight: %zu B of shared memory", smem);
+    p.a_rows = p.k_pad4 <= 64 ? 64 : 128;
+    // tile rows / operand buffers / raw stages: the deepest overlap that fits 227 KB
+    const int cand[6][3] = {{64, 2, 2}, {64, 2, 1}, {32, 2, 2}, {32, 2, 1}, {64, 1, 2}, {64, 1, 1}};
+    size_t smem = 0;
+    bool found = false;
+    for (int i = 0; i < 6 && !found; ++i) {
+        const int wr = cand[i][0], nb = cand[i][1], rs = cand[i][2];
+        const size_t rq = wr / 4;
+        const size_t ops1 = 2 * ((size_t)p.m_blocks * rq * (p.a_rows * 16 + 16)) + 2 * (rq * (p.n_pad * 16 + 16));
+        const size_t raw1 = (size_t)wr * (p.k_pad4 + p.n_pad) * 4;
+        const size_t total = nb * ops1 + rs * raw1 + 4 * 8 + 16 + 2048;     // +2 KB: the a_rows=64 overrun stays inside
+        if (total <= 227 * 1024) {
+            p.w_rows = wr; p.nbuf = nb; p.raw_stages = rs; smem = total; found = true;
+        }
+    }
+    EMER_REQUIRE(found, "emer_linear_tc_bwd_weight: layer %dx%d does not fit shared memory", k, n_out);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -847,10 +886,9 @@ extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const floa
         }
         configured = smem;
     }
-    const int64_t n_tiles = emer::ceil_div(n, WROWS);
-    const int ctas_per_sm = smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1);
-    int64_t grid = 148 * ctas_per_sm;
+    const int64_t n_tiles = emer::ceil_div(n, p.w_rows);
+    int64_t grid = 148;
     if (grid > n_tiles) grid = n_tiles;
-    tc_wgrad_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(p);
+    tc_wgrad_kernel<<<(unsigned)grid, NT_ALL, smem, (cudaStream_t)stream>>>(p);
     return emer::check_launch("emer_linear_tc_bwd_weight");
 }
