@@ -39,8 +39,8 @@ UNIT = "rays/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="static", choices=["static", "dynamic", "flow", "flow_feat"])
     ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step")
@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -351,17 +351,39 @@ def run_ours(args):
                   file=sys.stderr)
         print(f"# library kernels: {tot_ms / 3:.3f} ms/step of {ms / args.steps:.3f} ms/step", file=sys.stderr)
 
-    roof = None
-    if grid_dom is not None:
-        avg_ms = per_launch[grid_dom]
-        nbytes = _lib.algorithmic_bytes(grid_dom[1])
+    # measured per launch by `ncu --set full` (profiles/r1_grid_ncu_full_summary.csv): dram read + write
+    GRID_FWD_DRAM_TRAFFIC = {"D3L10F4_N524288": 266852096 + 92160256}
+
+    def layer_bytes(name, tag):
+        """Algorithmic HBM bytes of one dense-layer launch: rows * (inputs + outputs) * 4."""
+        import re
+
+        m = re.match(r"k(\d+)_o(\d+)_N(\d+)", tag)
+        if not m:
+            return None
+        k, o, n = (int(v) for v in m.groups())
+        return n * (k + o) * 4
+
+    def roofline_of(key):
+        name, tag = key
+        avg_ms = per_launch[key]
+        if name == "emer_grid_fwd":
+            nbytes, traffic = _lib.algorithmic_bytes(tag), GRID_FWD_DRAM_TRAFFIC.get(tag)
+        elif name.startswith("emer_linear"):
+            nbytes, traffic = layer_bytes(name, tag), None
+        else:
+            return None
+        if not nbytes:
+            return None
         ach = nbytes / (avg_ms / 1e3) / 1e9
-        roof = {"kernel": f"{grid_dom[0]}[{grid_dom[1]}]", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": avg_ms,
-                "launches_timed": table[grid_dom][0],
-                "share_of_library_kernel_time": table[grid_dom][1] / tot_ms,
+        return {"kernel": f"{name}[{tag}]", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": avg_ms, "launches_timed": table[key][0],
+                "share_of_library_kernel_time": table[key][1] / tot_ms,
                 "timing": "CUDA events around each launch, 3 eager steps after the timed region"}
+
+    roof = roofline_of(dom)                                  # the kernel with the largest share of the step
+    roof_grid = roofline_of(grid_dom) if grid_dom is not None else None   # the hash-grid gather (north star)
     dom_ms = per_launch[dom]
     by_name = {k: v[1] for k, v in table.items()}
     line = {
@@ -379,7 +401,7 @@ def run_ours(args):
                             "avg_launch_ms": dom_ms},
         "cuda_graph": tr.use_graph,
         "library_kernel_ms_per_step": tot_ms / 3,
-        "roofline": roof, "clocks": clk,
+        "roofline": roof if roof is not None else roof_grid, "roofline_hash_grid": roof_grid, "clocks": clk,
     }
     if e2e is not None:
         line["e2e"] = e2e
