@@ -19,26 +19,25 @@ namespace emer {
 
 constexpr int FT_DIR = 33;   // 3 identity + 5 octaves x (sin, sin(.+pi/2)) x 3
 
-__global__ void field_tail_fwd_kernel(const float* __restrict__ feats, int64_t ld_feats, int G,
-                                      const float* __restrict__ dirs, const int64_t* __restrict__ idx,
-                                      const float* __restrict__ emb, int E, float* __restrict__ out, int64_t ld_out,
-                                      float* __restrict__ sigma, int64_t n, int S) {
-    // one thread per (point, 4-float column group)
-    const int groups = (int)(ld_out / 4);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * groups) return;
-    const int64_t pt = t / groups;
-    const int c0 = (int)(t - pt * groups) * 4;
-    const int64_t ray = pt / S;
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c0 + j;
+// One CTA per ray: the per-ray tail (direction encoding + embedding row, <= 64 floats) is computed once
+// into shared memory, then the ray's S rows are written as 16-byte pieces: geo columns are a straight
+// float4 copy of the field features, tail columns a broadcast of the shared values.
+constexpr int FT_MAX_TAIL = 72;      // 33 + E (<= 32) + pad
+
+__global__ void __launch_bounds__(256) field_tail_fwd_kernel(const float* __restrict__ feats, int64_t ld_feats, int G,
+                                                              const float* __restrict__ dirs,
+                                                              const int64_t* __restrict__ idx,
+                                                              const float* __restrict__ emb, int E,
+                                                              float* __restrict__ out, int64_t ld_out,
+                                                              float* __restrict__ sigma, int64_t n_rays, int S) {
+    __shared__ __align__(16) float tail[FT_MAX_TAIL];
+    const int64_t ray = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n_tail = (int)ld_out - G;                      // includes the zero padding
+    if (tid < n_tail) {
         float x = 0.0f;
-        if (c < G) {
-            x = __ldg(feats + pt * ld_feats + c);
-        } else if (c < G + FT_DIR) {
-            const int e = c - G;                      // encoding index: [x(3) | sin(2^i x)(15) | sin(2^i x + pi/2)(15)]
+        if (tid < FT_DIR) {
+            const int e = tid;                                // [x(3) | sin(2^i x)(15) | sin(2^i x + pi/2)(15)]
             if (e < 3) {
                 x = (__ldg(dirs + ray * 3 + e) + 1.0f) / 2.0f;
             } else {
@@ -49,13 +48,28 @@ __global__ void field_tail_fwd_kernel(const float* __restrict__ feats, int64_t l
                 if (shifted) arg = arg + 0.5f * 3.14159265358979323846f;
                 x = sinf(arg);
             }
-        } else if (c < G + FT_DIR + E) {
-            x = __ldg(emb + __ldg(idx + ray) * E + (c - G - FT_DIR));
+        } else if (tid < FT_DIR + E) {
+            x = __ldg(emb + __ldg(idx + ray) * E + (tid - FT_DIR));
         }
-        v[j] = x;
+        tail[tid] = x;
     }
-    *reinterpret_cast<float4*>(out + pt * ld_out + c0) = make_float4(v[0], v[1], v[2], v[3]);
-    if (c0 == 0 && sigma) sigma[pt] = expf(v[0] - 1.0f);
+    __syncthreads();
+    const int quads = (int)(ld_out / 4), gq = G / 4;
+    const bool vec_in = (ld_feats % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
+    for (int e = tid; e < S * quads; e += 256) {
+        const int s = e / quads, q = e - s * quads;
+        const int64_t pt = ray * S + s;
+        float4 v;
+        if (q < gq) {
+            const float* src = feats + pt * ld_feats + q * 4;
+            if (vec_in) v = __ldg(reinterpret_cast<const float4*>(src));
+            else v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+            if (q == 0 && sigma) sigma[pt] = expf(v.x - 1.0f);
+        } else {
+            v = *reinterpret_cast<const float4*>(tail + (q - gq) * 4);
+        }
+        *reinterpret_cast<float4*>(out + pt * ld_out + q * 4) = v;
+    }
 }
 
 // d_rgb_in[:, 0] += d_sigma * exp(min(feats0 - 1, 15)); d_emb scatter.  One warp per ray.
@@ -97,10 +111,10 @@ extern "C" int emer_field_tail_fwd(const float* feats, int64_t ld_feats, int g_d
     EMER_REQUIRE(e_dim == 0 || (idx && emb), "emer_field_tail_fwd: embedding needs indices and a table");
     EMER_REQUIRE(ld_out % 4 == 0 && ld_out >= g_dim + FT_DIR + e_dim && ((uintptr_t)out & 15) == 0,
                  "emer_field_tail_fwd: output rows must be 16-byte aligned and wide enough");
-    const int64_t n = n_rays * n_samples;
-    const int64_t total = n * (ld_out / 4);
-    field_tail_fwd_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        feats, ld_feats, g_dim, dirs, idx, emb, e_dim, out, ld_out, sigma, n, n_samples);
+    EMER_REQUIRE(g_dim % 4 == 0 && ld_out - g_dim <= FT_MAX_TAIL, "emer_field_tail_fwd: geometry width %d must be a "
+                 "multiple of 4 and the tail at most %d floats", g_dim, FT_MAX_TAIL);
+    field_tail_fwd_kernel<<<(unsigned)n_rays, 256, 0, (cudaStream_t)stream>>>(
+        feats, ld_feats, g_dim, dirs, idx, emb, e_dim, out, ld_out, sigma, n_rays, n_samples);
     return check_launch("emer_field_tail_fwd");
 }
 

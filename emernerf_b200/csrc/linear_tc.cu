@@ -178,7 +178,6 @@ struct Params {
     int use_async;        // cp.async ring (16-byte aligned rows, no act' in the loader)
     int a_stages, raw_stages;   // ring depths chosen by the host
     int ring_bytes;             // operand ring area (>= the 34 816 B epilogue staging tile)
-    long long* dbg;       // optional phase timers (cycles) of CTA 0 / thread 0; NULL in production
 };
 
 // Warp-specialised: 8 converter/epilogue warps (NT = 256 threads) + 1 MMA-issuing warp.
@@ -498,7 +497,6 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-static long long* g_tc_dbg = nullptr;
 
 template <bool BWD, int ACT>
 static int launch_t(Params& p, size_t smem, int64_t grid, cudaStream_t st, const char* what) {
@@ -517,7 +515,6 @@ static int launch_t(Params& p, size_t smem, int64_t grid, cudaStream_t st, const
 
 template <bool BWD>
 static int launch(Params& p, cudaStream_t st, const char* what) {
-    p.dbg = g_tc_dbg;
     p.kred = BWD ? p.n_out : p.k;
     p.ncols = BWD ? p.k : p.n_out;
     p.kred_pad = round_up(p.kred, 8);
@@ -807,13 +804,6 @@ __global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
 }  // namespace emer
 
 using namespace emer;
-
-/* debugging hook (not part of the product ABI): device buffer of 10 int64 that CTA 0 of the next
- * tc_linear launches fills with per-phase cycle counts; NULL disables. */
-extern "C" int emer_debug_tc_timing(long long* device_buffer) {
-    tc::g_tc_dbg = device_buffer;
-    return 0;
-}
 
 extern "C" int emer_linear_tc_fwd(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
                                   int64_t n, int k, int n_out, int act, void* stream) {

@@ -121,10 +121,6 @@ int emer_linear_tc_bwd_data(const float* dy, int64_t lddy, const float* y, int64
 int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const float* dz, int64_t lddz, float* dw,
                               float* db, int64_t n, int k, int n_out, void* stream);
 
-/* Debug hook: device buffer of 10 int64 receiving per-phase cycle counters of CTA 0 of subsequent
- * emer_linear_tc_fwd / _bwd_data launches (NULL disables; production callers never set it). */
-int emer_debug_tc_timing(long long* device_buffer);
-
 /* ---- inverse-CDF resampling (replaces nerfacc.pdf.importance_sampling + _transform_stot,
  *      third_party/nerfacc_prop_net.py:153-160,172-175,299-339) ---------------------------- */
 enum { EMER_STOT_UNIFORM = 0, EMER_STOT_LINDISP = 1, EMER_STOT_SQRT = 2, EMER_STOT_LOG = 3,

@@ -380,3 +380,40 @@ def test_fused_proposal_level_vs_oracle(stratified):
     assert torch.equal(s_got.cpu(), iv.vals) and torch.equal(t_got.cpu(), t)
     assert rel_err(cdf_got, cdf_want) < 2e-5
     assert torch.equal(cdf_got[:, -1].cpu(), torch.ones(R))
+
+
+@pytest.mark.parametrize("with_emb,extra", [(True, 0), (True, 64), (False, 0)])
+def test_field_tail_forward_backward_vs_torch(with_emb, extra):
+    """Fused field tail vs the reference's op chain in plain PyTorch (CPU): density, [geo | dir | emb]
+    assembly, and the gradients w.r.t. the features and the embedding table."""
+    from emernerf_b200 import _ops
+    from oracle import hotpath
+
+    g = torch.Generator().manual_seed(2)
+    R, S, G, E = 37, 16, 64, 16
+    feats = torch.randn(R, S, G + extra, generator=g)
+    dirs = torch.randn(R, 3, generator=g)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    idx = torch.randint(0, 11, (R,), generator=g)
+    emb = torch.randn(11, E, generator=g)
+    g_sig = torch.randn(R, S, generator=g)
+    width = G + 33 + (E if with_emb else 0)
+    g_in = torch.randn(R, S, width, generator=g)
+
+    fo, eo = feats.clone().requires_grad_(True), emb.clone().requires_grad_(True)
+    sig_o = hotpath.density_activation(fo[..., 0])
+    h = hotpath.sinusoidal((dirs + 1.0) / 2.0)[:, None, :].expand(R, S, 33)
+    parts = [fo[..., :G], h] + ([torch.nn.functional.embedding(idx, eo)[:, None, :].expand(R, S, E)] if with_emb else [])
+    in_o = torch.cat(parts, -1)
+    ((sig_o * g_sig).sum() + (in_o * g_in).sum()).backward()
+
+    fg, eg = feats.to(DEV).requires_grad_(True), emb.to(DEV).requires_grad_(True)
+    sig, rgb_in = _ops.field_tail(fg, dirs.to(DEV), idx.to(DEV) if with_emb else None, eg if with_emb else None, G)
+    assert rgb_in.shape == (R, S, width)
+    ((sig * g_sig.to(DEV)).sum() + (rgb_in * g_in.to(DEV)).sum()).backward()
+    assert rel_err(sig, sig_o) < 2e-6
+    assert rel_err(rgb_in, in_o) < 2e-6          # sinf on device vs host: ulps
+    assert torch.equal(rgb_in[..., :G].cpu(), feats[..., :G])
+    assert rel_err(fg.grad, fo.grad) < 1e-5
+    if with_emb:
+        assert rel_err(eg.grad, eo.grad) < 1e-5
