@@ -369,6 +369,13 @@ def run_ours(args):
         avg_ms = per_launch[key]
         if name == "emer_grid_fwd":
             nbytes, traffic = _lib.algorithmic_bytes(tag), GRID_FWD_DRAM_TRAFFIC.get(tag)
+        elif name == "emer_grid_bwd":
+            # scatter: the corners are read-modify-written (2x the corner bytes), dy read once
+            import re
+
+            m = re.match(r"D(\d+)L(\d+)F(\d+)_N(\d+)", tag)
+            d_, l_, f_, n_ = (int(v) for v in m.groups())
+            nbytes, traffic = n_ * (2 * l_ * (2 ** d_) * f_ * 4 + d_ * 4 + l_ * f_ * 4), None
         elif name.startswith("emer_linear"):
             nbytes, traffic = layer_bytes(name, tag), None
         else:
