@@ -16,13 +16,15 @@
 // give identical results and MMA rate; MN-major tf32 operands without swizzle return zeros, so the
 // weight-gradient kernel transposes while staging and stays K-major.)
 //
-// One CTA = 128 threads = 128 rows = 128 TMEM lanes (thread t owns row t in the epilogue:
-// tcgen05.ld 32x32b, warp w reads lanes 32w..32w+31).  Global -> shared goes through a ring of
-// cp.async (LDGSTS) stages of raw fp32 -- bytes in flight do not depend on occupancy (the first
-// version loaded through registers and sat on long-scoreboard stalls at 12 % active warps, see
-// profiles/) -- then each thread converts exactly the 16-byte pieces it copied (no barrier needed
-// between copy and convert), and one elected thread issues the MMAs.  Completion is tracked with
-// mbarriers armed by tcgen05.commit.
+// One CTA = 128 rows = 128 TMEM lanes, 9 warps: 8 converter/epilogue warps (warps w and w+4 share TMEM
+// lane quadrant w: tcgen05.ld 32x32b) and one MMA-issuing warp.  Global -> shared goes through a ring of
+// cp.async (LDGSTS) stages of raw fp32 -- bytes in flight do not depend on occupancy (the first version
+// loaded through registers and sat on long-scoreboard stalls at 12 % active warps, see profiles/) --
+// then each converter thread splits exactly the 16-byte pieces it copied (no barrier between copy and
+// convert) into the hi/lo operand stage and arrives on its `full` mbarrier; the issuer waits, issues the
+// MMAs and releases the stage with tcgen05.commit -> `empty`.  A tcgen05.mma costs its issuing thread
+// ~100 cycles (measured), which is why it has a warp of its own.  The epilogue goes TMEM -> registers ->
+// (bias, activation) -> shared staging tile -> coalesced 16-byte stores (-> optional ReLU mask).
 //
 //   forward        Y  = act(X W^T + b)                  A = X[128 x k],      B = W   [n_out x k]
 //   backward-data  dX = dZ W   (* relu-mask epilogue)   A = dZ[128 x n_out], B = W^T [k x n_out]

@@ -148,3 +148,50 @@ def test_image_shaped_batches_round_trip():
         out = render_rays(field, est, props, img, cases.render_cfg())
     assert out["rgb"].shape == (6, 8, 3) and out["depth"].shape == (6, 8, 1)
     assert torch.equal(out["rgb"].reshape(-1, 3), flat["rgb"])
+
+
+def test_query_flow_and_attributes_agree_with_forward():
+    """The point-query entry points the evaluation code uses (train_emernerf.py:266-272,
+    datasets/metrics.py:276-300) return the same tensors as ``forward`` on the same points."""
+    g, field, props, est = _build("flow_feat")
+    field.eval()
+    gen = torch.Generator().manual_seed(4)
+    pos = (torch.rand(257, 3, generator=gen) * torch.tensor([100.0, 80.0, 20.0]) + torch.tensor([-20.0, -40.0, 0.0])).to(DEV)
+    t = torch.rand(257, generator=gen).to(DEV)
+    with torch.no_grad():
+        full = field(pos, None, {"normed_timestamps": t}, combine_static_dynamic=True, query_pe_head=False)
+        flow = field.query_flow(pos, t)
+        attr = field.query_attributes(pos, t)
+    assert torch.equal(flow["forward_flow"], full["forward_flow"])
+    assert torch.equal(flow["backward_flow"], full["backward_flow"])
+    for k in ("density", "static_density", "dynamic_density", "static_dino_feat", "dynamic_dino_feat"):
+        assert torch.equal(attr[k], full[k]), k
+    want = (full["static_density"].unsqueeze(-1) * full["static_dino_feat"]
+            + full["dynamic_density"].unsqueeze(-1) * full["dynamic_dino_feat"]) / (full["density"].unsqueeze(-1) + 1e-6)
+    assert rel_err(attr["dino_feat"], want) < 1e-6
+    # query_flow's density comes from the un-aggregated dynamic features (radiance_field.py:700-712)
+    assert flow["dynamic_density"].shape == (257,)
+
+
+def test_density_field_generic_call_matches_fused_level():
+    """DensityField.forward on explicit points (the closure path) and the fused proposal-level kernel see
+    the same network: CDFs agree to 2e-5."""
+    from emernerf_b200 import _ops
+    from emernerf_b200.third_party.nerfacc_prop_net import s_bounds
+
+    g, field, props, est = _build("static")
+    batch = g.tensors("in/pixel", DEV)
+    net = props[1]
+    R, n = batch["origins"].shape[0], 32
+    base = torch.arange(2, device=DEV, dtype=torch.float32).repeat(R, 1)
+    s_min, s_max = s_bounds("uniform_lindisp", cases.NEAR, cases.FAR)
+    lin = [m for m in net.base_mlp if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        s, t, cdf = _ops.prop_level(base, base, n, None, s_min, s_max, "uniform_lindisp", batch["origins"],
+                                    batch["viewdirs"], net.aabb, True, net.xyz_encoder.desc,
+                                    net.xyz_encoder.tcnn_encoding.params, lin[0].weight, lin[0].bias, lin[1].weight,
+                                    lin[1].bias)
+        pos = batch["origins"][:, None, :] + batch["viewdirs"][:, None, :] * (t[:, :-1] + t[:, 1:])[..., None] / 2.0
+        sigma = net(pos)["density"].squeeze(-1)
+        cdf2 = _ops.composite(t[:, :-1].contiguous(), t[:, 1:].contiguous(), sigma, want_cdf=True)[5]
+    assert rel_err(cdf, cdf2) < 2e-5
