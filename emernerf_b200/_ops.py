@@ -341,7 +341,9 @@ class _MLPChain(torch.autograd.Function):
                 dx = d_inp[:, :k]
         if need_x:
             if dx_skip is not None:
-                dx = dx + dx_skip
+                # sum into the skip slice of the [n, pad4] gradient buffer: rows stay 16-byte aligned for
+                # the consumer (no re-padding copy downstream)
+                dx = dx_skip.add_(dx)
             dx = dx.reshape(x_shape)
         out = [dx if need_x else None, None, None, None]
         for i in range(L):
