@@ -24,6 +24,7 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 # same library -- this is a debugging switch, not a backend dispatch.
 LINEAR_IMPL = os.environ.get("EMER_LINEAR", "tc")
 LINEAR_WGRAD_IMPL = os.environ.get("EMER_LINEAR_WGRAD", "tc")
+SKIP_BWD_IMPL = os.environ.get("EMER_SKIP_BWD", "stack")   # "stack": one stacked product; "add": two + add
 TC_MIN_ROWS = 1024          # tiny per-ray heads are launch-bound either way
 STOT_KINDS = {"uniform": 0, "lindisp": 1, "sqrt": 2, "log": 3, "uniform_lindisp": 4, "uniform_lindisp_0": 5}
 
@@ -254,7 +255,8 @@ class _MLPChain(torch.autograd.Function):
     activation-derivative pass ever runs on its own."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, skip_layer: int, out_act: int, has_bias: bool, *params: Tensor):
+    def forward(ctx, x: Tensor, catbuf: Optional[Tensor], skip_layer: int, out_act: int, has_bias: bool,
+                *params: Tensor):
         ctx.set_materialize_grads(False)
         ws = [_f32c(w) for w in (params[0::2] if has_bias else params)]
         bs = [_f32c(b) for b in params[1::2]] if has_bias else [None] * len(ws)
@@ -267,21 +269,29 @@ class _MLPChain(torch.autograd.Function):
         L = len(ws)
         inputs, lds, outs = [], [], []
         cur, ld = x2, ldx
+        shared = False           # x already sits behind the hidden columns of the caller's concat buffer
         for i, (w, b) in enumerate(zip(ws, bs)):
             n_out, k = w.shape
             if i == skip_layer and i > 0:
-                # cur is catbuf[:, :h] (written by layer i-1); the chain input goes behind it
+                # cur is cat[:, :h] (written by layer i-1); the chain input goes behind it
                 h = ws[i - 1].shape[0]
-                catbuf = cur._base if cur._base is not None else cur
-                catbuf[:, h:h + k0].copy_(x2)
-                cur, ld = catbuf[:, :h + k0], catbuf.shape[1]
+                cat = cur._base if cur._base is not None else cur
+                if not shared:
+                    cat[:, h:h + k0].copy_(x2)
+                cur, ld = cat[:, :h + k0], cat.shape[1]
             if cur.shape[1] != k:
                 raise ValueError(f"mlp layer {i}: input width {cur.shape[1]} != weight width {k}")
             act = ACT_RELU if i < L - 1 else out_act
             if i + 1 == skip_layer and i + 1 < L:
-                buf = torch.empty((n, _pad4(n_out + k0)), dtype=torch.float32, device=dev)
-                if buf.shape[1] > n_out + k0:
-                    buf[:, n_out + k0:].zero_()
+                shared = (catbuf is not None and catbuf.dim() == 2 and catbuf.is_contiguous()
+                          and catbuf.dtype == torch.float32 and tuple(catbuf.shape) == (n, _pad4(n_out + k0))
+                          and x2.data_ptr() == catbuf.data_ptr() + 4 * n_out and ldx == catbuf.shape[1])
+                if shared:
+                    buf = catbuf
+                else:
+                    buf = torch.empty((n, _pad4(n_out + k0)), dtype=torch.float32, device=dev)
+                    if buf.shape[1] > n_out + k0:
+                        buf[:, n_out + k0:].zero_()
                 y, ldy = buf[:, :n_out], buf.shape[1]
             else:
                 y = torch.empty((n, n_out), dtype=torch.float32, device=dev)
@@ -298,13 +308,14 @@ class _MLPChain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         skip_layer, out_act, has_bias, L, lds, k0, x_shape = ctx.meta
-        n_grads = 4 + (2 * L if has_bias else L)
+        n_grads = _CHAIN_ARGS + (2 * L if has_bias else L)
         if dy is None:
             return (None,) * n_grads
         saved = ctx.saved_tensors
         inputs, y_last, ws = saved[:L], saved[L], saved[L + 1:]
         n = inputs[0].shape[0]
         n_last = ws[-1].shape[0]
+        dev = y_last.device
         dz, lddz = _rows(dy, n_last)
         if out_act == ACT_SIGMOID:
             dz = dz * (y_last * (1.0 - y_last))
@@ -319,24 +330,46 @@ class _MLPChain(torch.autograd.Function):
         grads_b = [None] * L
         dx = None
         dx_skip = None
+        # Skip in front of layer 1 (the reference's heads): dX = dZ0 W0 + dZ1 W1[:, h:] is ONE product
+        # [dZ0 | dZ1] [W0 ; W1[:, h:]], so dZ1 and dZ0 are written side by side into ``gcat`` and the skip
+        # layer's data gradient only computes its hidden columns: no [n, k0] partial result, no add pass.
+        h0, n1 = ws[0].shape[0], (ws[1].shape[0] if L > 1 else 0)
+        stacked = (SKIP_BWD_IMPL == "stack" and skip_layer == 1 and L >= 3 and need_x and h0 % 4 == 0
+                   and n1 % 4 == 0 and h0 + n1 <= 128 and k0 <= 128)
+        gcat = torch.empty((n, h0 + n1), dtype=torch.float32, device=dev) if stacked else None
         for i in range(L - 1, -1, -1):
             w = ws[i]
             n_out, k = w.shape
             inp, ld = inputs[i], lds[i]
-            w_idx = 4 + (2 * i if has_bias else i)
+            w_idx = _CHAIN_ARGS + (2 * i if has_bias else i)
             if ctx.needs_input_grad[w_idx] or (has_bias and ctx.needs_input_grad[w_idx + 1]):
                 grads_w[i], grads_b[i] = _layer_bwd_weight(inp, ld, dz, lddz, w, has_bias, n)
             if i == 0 and not need_x:
                 break
-            if i > 0:
-                d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dz.device)
+            if stacked and i == 2:
+                # dZ1 = relu'(h1) * (dZ2 W2)  ->  gcat[:, h0:]
+                d_inp = gcat[:, h0:]
+                _layer_bwd_data(dz, lddz, w, d_inp, gcat.shape[1], n, inp, ld, n1)
+                dz, lddz = d_inp, gcat.shape[1]
+            elif stacked and i == 1:
+                # dZ0 = relu'(h0) * (dZ1 W1[:, :h0])  ->  gcat[:, :h0]
+                d_inp = gcat[:, :h0]
+                _layer_bwd_data(dz, lddz, w[:, :h0].contiguous(), d_inp, gcat.shape[1], n, inp, ld, h0)
+                dz, lddz = d_inp, gcat.shape[1]
+            elif stacked and i == 0:
+                w_stack = torch.cat([w, ws[1][:, h0:h0 + k0]], dim=0)
+                d_inp = torch.empty((n, _pad4(k0)), dtype=torch.float32, device=dev)
+                _layer_bwd_data(gcat, gcat.shape[1], w_stack, d_inp, d_inp.shape[1], n, None, 0, 0)
+                dx = d_inp[:, :k0]
+            elif i > 0:
+                d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dev)
                 h = ws[i - 1].shape[0]          # first h columns of this layer's input are ReLU outputs
                 _layer_bwd_data(dz, lddz, w, d_inp, d_inp.shape[1], n, inp, ld, h)
                 if i == skip_layer:
                     dx_skip = d_inp[:, h:h + k0]
                 dz, lddz = d_inp[:, :h], d_inp.shape[1]
             else:
-                d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dz.device)
+                d_inp = torch.empty((n, _pad4(k)), dtype=torch.float32, device=dev)
                 _layer_bwd_data(dz, lddz, w, d_inp, d_inp.shape[1], n, None, 0, 0)
                 dx = d_inp[:, :k]
         if need_x:
@@ -345,7 +378,7 @@ class _MLPChain(torch.autograd.Function):
                 # the consumer (no re-padding copy downstream)
                 dx = dx_skip.add_(dx)
             dx = dx.reshape(x_shape)
-        out = [dx if need_x else None, None, None, None]
+        out = [dx if need_x else None] + [None] * (_CHAIN_ARGS - 1)
         for i in range(L):
             out.append(grads_w[i])
             if has_bias:
@@ -353,17 +386,23 @@ class _MLPChain(torch.autograd.Function):
         return tuple(out)
 
 
-def mlp_chain(x: Tensor, weights, biases=None, out_act: int = ACT_NONE, skip_layer: int = -1) -> Tensor:
+_CHAIN_ARGS = 5           # x, catbuf, skip_layer, out_act, has_bias come before the parameters
+
+
+def mlp_chain(x: Tensor, weights, biases=None, out_act: int = ACT_NONE, skip_layer: int = -1,
+              catbuf: Optional[Tensor] = None) -> Tensor:
     """Evaluate a ReLU MLP head.  ``weights[i]``: [n_out_i, k_i] (nn.Linear layout); ``skip_layer``: the
-    layer in front of which [hidden, x] is concatenated (-1: none)."""
+    layer in front of which [hidden, x] is concatenated (-1: none).  ``catbuf`` (optional): the
+    [n, pad4(hidden + k)] buffer whose columns [hidden, hidden + k) ARE x (see :func:`field_tail`); the layer
+    before the skip then writes its output into the front columns and the concatenation is free."""
     if x.shape[-1] != weights[0].shape[1]:
         raise ValueError(f"mlp: input width {x.shape[-1]} != first layer width {weights[0].shape[1]}")
     if biases is None:
-        return _MLPChain.apply(x, skip_layer, out_act, False, *weights)
+        return _MLPChain.apply(x, catbuf, skip_layer, out_act, False, *weights)
     flat = []
     for w, b in zip(weights, biases):
         flat += [w, b]
-    return _MLPChain.apply(x, skip_layer, out_act, True, *flat)
+    return _MLPChain.apply(x, catbuf, skip_layer, out_act, True, *flat)
 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor], act: int = ACT_NONE) -> Tensor:
@@ -393,7 +432,9 @@ class _FieldTail(torch.autograd.Function):
     rgb_in [R, S, G+33+E] laid out [geo | dir encoding | embedding] in rows padded to 16 bytes)."""
 
     @staticmethod
-    def forward(ctx, feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional[Tensor], g_dim: int):
+    def forward(ctx, feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional[Tensor], g_dim: int,
+                front: int):
+        ctx.set_materialize_grads(False)
         _need_cuda(feats, dirs)
         r, s_, width_in = feats.shape
         f2, ldf = _rows(feats, width_in)
@@ -402,17 +443,21 @@ class _FieldTail(torch.autograd.Function):
         embc = None if emb is None else _f32c(emb)
         idxc = None if idx is None else idx.to(torch.int64).contiguous()
         width = g_dim + FT_DIR + e_dim
-        ld = _pad4(width)
-        out = torch.empty((r * s_, ld), dtype=torch.float32, device=feats.device)
+        # ``front`` spare columns ahead of every row: the colour head writes its first hidden layer there, which
+        # makes this buffer the [hidden | input] skip concatenation without a copy (see _MLPChain)
+        ld = _pad4(front + width)
+        buf = torch.empty((r * s_, ld), dtype=torch.float32, device=feats.device)
+        out = buf[:, front:front + width]
         sigma = torch.empty((r, s_), dtype=torch.float32, device=feats.device)
         _lib.call("emer_field_tail_fwd", _ptr(f2), ldf, g_dim, _ptr(dirs), _ptr(idxc), _ptr(embc), e_dim, _ptr(out), ld,
                   _ptr(sigma), r, s_, _stream())
         ctx.save_for_backward(f2, idxc)
-        ctx.meta = (ldf, g_dim, e_dim, width, ld, r, s_, width_in, None if emb is None else emb.shape)
-        return sigma, out.view(r, s_, ld)[..., :width]
+        ctx.meta = (ldf, g_dim, e_dim, width, _pad4(width), r, s_, width_in, None if emb is None else emb.shape)
+        ctx.mark_non_differentiable(buf)
+        return sigma, out.view(r, s_, width), buf
 
     @staticmethod
-    def backward(ctx, d_sigma, d_rgb_in):
+    def backward(ctx, d_sigma, d_rgb_in, _d_buf=None):
         f2, idxc = ctx.saved_tensors
         ldf, g_dim, e_dim, width, ld, r, s_, width_in, emb_shape = ctx.meta
         n = r * s_
@@ -432,11 +477,16 @@ class _FieldTail(torch.autograd.Function):
         d_feats = g2[:, :g_dim]
         if width_in > g_dim:
             d_feats = torch.nn.functional.pad(d_feats, (0, width_in - g_dim))
-        return d_feats.reshape(r, s_, width_in), None, None, d_emb, None
+        return d_feats.reshape(r, s_, width_in), None, None, d_emb, None, None
 
 
-def field_tail(feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional[Tensor], g_dim: int):
-    return _FieldTail.apply(feats, dirs, idx, emb, g_dim)
+def field_tail(feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional[Tensor], g_dim: int, front: int = 0):
+    """(sigma, rgb_in) -- or (sigma, rgb_in, catbuf) with ``front`` > 0, where rgb_in = catbuf[:, front:front+width]
+    and catbuf is handed to :func:`mlp_chain` so that the head's skip concatenation needs no copy."""
+    if front % 4:
+        raise ValueError("field_tail: front must be a multiple of 4 (16-byte aligned rows)")
+    sigma, rgb_in, buf = _FieldTail.apply(feats, dirs, idx, emb, g_dim, front)
+    return (sigma, rgb_in, buf) if front else (sigma, rgb_in)
 
 
 # ----------------------------------------------------------------------------- sampling

@@ -28,12 +28,12 @@ __global__ void __launch_bounds__(256) field_tail_fwd_kernel(const float* __rest
                                                               const float* __restrict__ dirs,
                                                               const int64_t* __restrict__ idx,
                                                               const float* __restrict__ emb, int E,
-                                                              float* __restrict__ out, int64_t ld_out,
+                                                              float* __restrict__ out, int64_t ld_out, int out_cols,
                                                               float* __restrict__ sigma, int64_t n_rays, int S) {
     __shared__ __align__(16) float tail[FT_MAX_TAIL];
     const int64_t ray = blockIdx.x;
     const int tid = threadIdx.x;
-    const int n_tail = (int)ld_out - G;                      // includes the zero padding
+    const int n_tail = out_cols - G;                         // includes the zero padding
     if (tid < n_tail) {
         float x = 0.0f;
         if (tid < FT_DIR) {
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) field_tail_fwd_kernel(const float* __rest
         tail[tid] = x;
     }
     __syncthreads();
-    const int quads = (int)(ld_out / 4), gq = G / 4;
+    const int quads = out_cols / 4, gq = G / 4;
     const bool vec_in = (ld_feats % 4 == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15) == 0);
     for (int e = tid; e < S * quads; e += 256) {
         const int s = e / quads, q = e - s * quads;
@@ -111,10 +111,13 @@ extern "C" int emer_field_tail_fwd(const float* feats, int64_t ld_feats, int g_d
     EMER_REQUIRE(e_dim == 0 || (idx && emb), "emer_field_tail_fwd: embedding needs indices and a table");
     EMER_REQUIRE(ld_out % 4 == 0 && ld_out >= g_dim + FT_DIR + e_dim && ((uintptr_t)out & 15) == 0,
                  "emer_field_tail_fwd: output rows must be 16-byte aligned and wide enough");
-    EMER_REQUIRE(g_dim % 4 == 0 && ld_out - g_dim <= FT_MAX_TAIL, "emer_field_tail_fwd: geometry width %d must be a "
+    // columns [0, out_cols) of every row are written (the padding with zeros); ld_out is only the row stride,
+    // so the rows may live inside a wider buffer (the rgb head's skip-concatenation buffer)
+    const int out_cols = (g_dim + FT_DIR + e_dim + 3) / 4 * 4;
+    EMER_REQUIRE(g_dim % 4 == 0 && out_cols - g_dim <= FT_MAX_TAIL, "emer_field_tail_fwd: geometry width %d must be a "
                  "multiple of 4 and the tail at most %d floats", g_dim, FT_MAX_TAIL);
     field_tail_fwd_kernel<<<(unsigned)n_rays, 256, 0, (cudaStream_t)stream>>>(
-        feats, ld_feats, g_dim, dirs, idx, emb, e_dim, out, ld_out, sigma, n_rays, n_samples);
+        feats, ld_feats, g_dim, dirs, idx, emb, e_dim, out, ld_out, out_cols, sigma, n_rays, n_samples);
     return check_launch("emer_field_tail_fwd");
 }
 

@@ -211,9 +211,19 @@ class RadianceField(nn.Module):
             idx, emb = t[:, 0], self.appearance_embedding.weight
         return directions[:, 0], idx, emb
 
-    def _rgb_from_tail(self, rgb_in: Tensor) -> Tensor:
+    def _field_tail(self, feats: Tensor, tail) -> Tuple[Tensor, Tuple[Tensor, Tensor]]:
+        """density and the colour head's input; the input rows are laid out behind ``front`` spare columns so
+        that they already are the [hidden | input] skip concatenation of the head's second layer."""
+        front = self.rgb_head.layers[0].out_features
+        if front % 4 or len(self.rgb_head.layers) < 2:
+            front = 0
+        res = _ops.field_tail(feats, *tail, self.geometry_feature_dim, front=front)
+        return res[0], (res[1], res[2] if front else None)
+
+    def _rgb_from_tail(self, tail_out: Tuple[Tensor, Optional[Tensor]]) -> Tensor:
         """rgb head on a [geo | dir | emb] input: the reference order is [dir | emb | geo]
         (radiance_field.py:647), so the weight columns that multiply the input are permuted."""
+        rgb_in, catbuf = tail_out
         G = self.geometry_feature_dim
         tail = rgb_in.shape[-1] - G
         key = (G, tail, str(rgb_in.device))
@@ -225,7 +235,7 @@ class RadianceField(nn.Module):
             self._perm_key = key
         l0, l1, l2 = self.rgb_head.layers
         return _ops.mlp_chain(rgb_in, [l0.weight[:, self._perm0], l1.weight[:, self._perm1], l2.weight],
-                              [l0.bias, l1.bias, l2.bias], _ops.ACT_SIGMOID, 1)
+                              [l0.bias, l1.bias, l2.bias], _ops.ACT_SIGMOID, 1, catbuf=catbuf)
 
     # ------------------------------------------------------------------ building blocks
     def contract_points(self, positions: Tensor) -> Tensor:
@@ -287,7 +297,7 @@ class RadianceField(nn.Module):
         geo, sem = feats[..., :G], feats[..., G:G + S]
         tail = None if (return_density_only or feats.dim() != 3) else self._tail_inputs(directions, data_dict)
         if tail is not None:
-            static_density, rgb_in_static = _ops.field_tail(feats, *tail, G)
+            static_density, rgb_in_static = self._field_tail(feats, tail)
         else:
             static_density = self._density(feats)
 
@@ -306,7 +316,7 @@ class RadianceField(nn.Module):
                 out.update(agg)
             dyn_geo, dyn_sem = dyn_feats[..., :G], dyn_feats[..., G:G + S]
             if tail is not None:
-                dynamic_density, rgb_in_dynamic = _ops.field_tail(dyn_feats, *tail, G)
+                dynamic_density, rgb_in_dynamic = self._field_tail(dyn_feats, tail)
             else:
                 dynamic_density = self._density(dyn_feats)
             density = static_density + dynamic_density

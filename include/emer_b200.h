@@ -144,7 +144,9 @@ int emer_prop_level(const emer_grid_desc* g, const float* prev_s, const float* p
                     float* out_t, float* out_cdf, int64_t n_rays, void* stream);
 
 /* ---- field tail: between the base MLP and the colour head (radiance_field.py:417-422,622-647) ---
- * forward : out[n, :] = [feats[n, 0:G] | sinenc((dir[ray]+1)/2) (33) | emb[idx[ray]] (E) | 0-pad]   (ld_out % 4 == 0)
+ * forward : out[n, 0:W4] = [feats[n, 0:G] | sinenc((dir[ray]+1)/2) (33) | emb[idx[ray]] (E) | 0-pad], W4 = G+33+E
+ *           rounded up to 4; ld_out (% 4 == 0, >= W4) is only the row stride, so the rows may sit inside a
+ *           wider buffer (the colour head's skip-concatenation buffer) and no copy is needed later
  *           sigma[n] = exp(feats[n, 0] - 1)     (may be NULL);  n = ray * n_samples + sample
  * backward: d_out[:, 0] += d_sigma * exp(min(feats0 - 1, 15)) in place (so d_out[:, 0:G] IS d_feats);
  *           d_emb[idx[ray], :] += sum_s d_out[ray, s, G+33 : G+33+E]  (atomics, caller zeroes; may be NULL) */

@@ -382,8 +382,9 @@ def test_fused_proposal_level_vs_oracle(stratified):
     assert torch.equal(cdf_got[:, -1].cpu(), torch.ones(R))
 
 
-@pytest.mark.parametrize("with_emb,extra", [(True, 0), (True, 64), (False, 0)])
-def test_field_tail_forward_backward_vs_torch(with_emb, extra):
+@pytest.mark.parametrize("with_emb,extra,front", [(True, 0, 0), (True, 64, 0), (False, 0, 0), (True, 0, 64),
+                                                  (False, 64, 32)])
+def test_field_tail_forward_backward_vs_torch(with_emb, extra, front):
     """Fused field tail vs the reference's op chain in plain PyTorch (CPU): density, [geo | dir | emb]
     assembly, and the gradients w.r.t. the features and the embedding table."""
     from emernerf_b200 import _ops
@@ -408,8 +409,17 @@ def test_field_tail_forward_backward_vs_torch(with_emb, extra):
     ((sig_o * g_sig).sum() + (in_o * g_in).sum()).backward()
 
     fg, eg = feats.to(DEV).requires_grad_(True), emb.to(DEV).requires_grad_(True)
-    sig, rgb_in = _ops.field_tail(fg, dirs.to(DEV), idx.to(DEV) if with_emb else None, eg if with_emb else None, G)
+    res = _ops.field_tail(fg, dirs.to(DEV), idx.to(DEV) if with_emb else None, eg if with_emb else None, G,
+                          front=front)
+    sig, rgb_in = res[0], res[1]
     assert rgb_in.shape == (R, S, width)
+    if front:
+        # rows sit behind ``front`` spare columns of the concat buffer handed to the colour head
+        catbuf = res[2]
+        assert catbuf.shape == (R * S, (front + width + 3) // 4 * 4) and not catbuf.requires_grad
+        assert rgb_in.data_ptr() == catbuf.data_ptr() + 4 * front
+        assert torch.equal(catbuf[:, front:front + width], rgb_in.reshape(R * S, width))
+        assert (catbuf[:, front + width:] == 0).all()
     ((sig * g_sig.to(DEV)).sum() + (rgb_in * g_in.to(DEV)).sum()).backward()
     assert rel_err(sig, sig_o) < 2e-6
     assert rel_err(rgb_in, in_o) < 2e-6          # sinf on device vs host: ulps
@@ -417,3 +427,50 @@ def test_field_tail_forward_backward_vs_torch(with_emb, extra):
     assert rel_err(fg.grad, fo.grad) < 1e-5
     if with_emb:
         assert rel_err(eg.grad, eo.grad) < 1e-5
+
+
+@pytest.mark.parametrize("impl", ["stack", "add"])
+@pytest.mark.parametrize("shared", [False, True])
+@pytest.mark.parametrize("n", [300, 128 * 70 + 19])
+def test_colour_head_chain_skip_variants(impl, shared, n, monkeypatch):
+    """The colour head (113 -> 64 -> [64 | 113] -> 64 -> 3, sigmoid; radiance_fields/mlp.py:38-46) through the
+    chain in its four bookkeeping variants -- stacked / two-product skip gradient, shared / copied
+    concatenation buffer -- against fp64 autograd.  n = 300 runs the CUDA-core layers, the larger n the
+    tcgen05 ones (3xTF32: ~1e-6)."""
+    from emernerf_b200 import _ops
+
+    monkeypatch.setattr(_ops, "SKIP_BWD_IMPL", impl)
+    g = torch.Generator().manual_seed(5)
+    k0, h = 113, 64
+    dims = [(h, k0), (h, h + k0), (3, h)]
+    ws = [(torch.randn(o, k, generator=g) / k ** 0.5) for o, k in dims]
+    bs = [torch.randn(o, generator=g) * 0.1 for o, _ in dims]
+    x = torch.randn(n, k0, generator=g)
+    up = torch.randn(n, 3, generator=g)
+
+    wd = [w.double().requires_grad_() for w in ws]
+    bd = [b.double().requires_grad_() for b in bs]
+    xd = x.double().requires_grad_()
+    h1 = torch.relu(xd @ wd[0].t() + bd[0])
+    h2 = torch.relu(torch.cat([h1, xd], -1) @ wd[1].t() + bd[1])
+    yd = torch.sigmoid(h2 @ wd[2].t() + bd[2])
+    (yd * up.double()).sum().backward()
+
+    wg = [w.to(DEV).requires_grad_() for w in ws]
+    bg = [b.to(DEV).requires_grad_() for b in bs]
+    catbuf = None
+    if shared:
+        catbuf = torch.zeros(n, (h + k0 + 3) // 4 * 4, device=DEV)
+        catbuf[:, h:h + k0] = x.to(DEV)
+        xg = catbuf[:, h:h + k0].detach().requires_grad_()      # same memory, a leaf for dX
+        assert xg.data_ptr() == catbuf.data_ptr() + 4 * h
+    else:
+        xg = x.to(DEV).requires_grad_()
+    y = _ops.mlp_chain(xg, wg, bg, _ops.ACT_SIGMOID, 1, catbuf=catbuf)
+    (y * up.to(DEV)).sum().backward()
+    if shared:
+        assert rel_err(catbuf[:, :h], h1.detach()) < 5e-6       # layer 0 wrote into the shared buffer
+    assert rel_err(y, yd.detach()) < 5e-6
+    assert rel_err(xg.grad, xd.grad) < 2e-5
+    for a, b in zip(wg + bg, wd + bd):
+        assert rel_err(a.grad, b.grad) < 2e-5
