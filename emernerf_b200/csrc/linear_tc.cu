@@ -40,10 +40,9 @@ constexpr int ROWS = 128;
 constexpr int CHUNK = 32;                    // k per pipeline stage
 constexpr int A_PANEL = ROWS * 16 + 16;      // 2064 B (padded LBO)
 constexpr int A_STAGE = (CHUNK / 4) * A_PANEL;   // one of hi / lo: 16512 B
-constexpr int A_STAGES = 2;                  // operand ring
 constexpr int RAW_STAGE = ROWS * CHUNK * 4;  // 16 KB of raw fp32 per chunk
-constexpr int RAW_STAGES = 4;                // cp.async ring depth
-constexpr int NT = 256;                      // threads per CTA: 8 warps convert, warps w and w+4 share a TMEM lane quadrant
+constexpr int NT = 256;                      // converter threads of a multi-CTA-per-SM launch (512 when one CTA owns the SM);
+                                             // warps w, w+4, ... share TMEM lane quadrant w
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -182,24 +181,24 @@ struct Params {
     int ring_bytes;             // operand ring area (>= the 34 816 B epilogue staging tile)
 };
 
-// Warp-specialised: 8 converter/epilogue warps (NT = 256 threads) + 1 MMA-issuing warp.
+// Warp-specialised: NTC / 32 (8 or 16) converter/epilogue warps + 1 MMA-issuing warp.
 //   converters : cp.async raw ring -> split hi/lo -> operand stage s -> arrive full[s]
 //                ... last chunk of a tile: wait accum -> epilogue -> arrive acc_free
 //   issuer     : wait full[s] -> 3 tcgen05.mma per k-step -> commit empty[s] (and accum on the last chunk)
 // so the ~100 cycles each tcgen05.mma costs its issuing thread (phase timers, profiles/) no longer sit
 // on the converters' critical path.  a_stages / raw_stages / ring_bytes are picked by the host so that
 // 2-3 CTAs share an SM whenever shared memory allows.
-constexpr int NT_ALL = NT + 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void conv_sync() {        // barrier among the 256 converter threads only
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+template <int NTC>
+__device__ __forceinline__ void conv_sync() {        // barrier among the converter threads only
+    asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory");
 }
 
-template <bool BWD, int ACT>
-__global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
+template <bool BWD, int ACT, int NTC>
+__global__ void __launch_bounds__(NTC + 32) tc_linear_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [B_hi | B_lo | operand ring / epilogue staging | raw ring | bias | barriers]
     const int b_panel = p.n_pad * 16;
@@ -218,15 +217,15 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const bool is_issuer = warp == NT / 32;
+    const bool is_issuer = warp == NTC / 32;
 
     if (tid == 0) {
-        mbar_init(&full_bar[0], NT);
-        mbar_init(&full_bar[1], NT);
+        mbar_init(&full_bar[0], NTC);
+        mbar_init(&full_bar[1], NTC);
         mbar_init(&empty_bar[0], 1);
         mbar_init(&empty_bar[1], 1);
         mbar_init(accum_bar, 1);
-        mbar_init(accfree_bar, NT);
+        mbar_init(accfree_bar, NTC);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -239,9 +238,9 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
     const int total = my_tiles * n_chunks;
     const int a_stages = p.a_stages, raw_stages = p.raw_stages;
 
-    constexpr int PIECES = ROWS * (CHUNK / 4) / NT;     // 4
-    const int my_r = (tid & (NT - 1)) >> 3, my_q = tid & 7;
-    const int64_t piece_stride = (int64_t)(NT / 8) * p.lda;
+    constexpr int PIECES = ROWS * (CHUNK / 4) / NTC;     // 4
+    const int my_r = (tid & (NTC - 1)) >> 3, my_q = tid & 7;
+    const int64_t piece_stride = (int64_t)(NTC / 8) * p.lda;
     const float* thread_base = p.a + (int64_t)my_r * p.lda + my_q * 4;
     int i_tl = 0, i_c = 0, i_stage = 0;
     auto issue_next = [&]() {
@@ -252,8 +251,8 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
         const int64_t rows_left = p.n - row0 - my_r;
 #pragma unroll
         for (int i = 0; i < PIECES; ++i) {
-            const bool ok = kok && (i * (NT / 8) < rows_left);
-            cp_async16(dst + i * NT * 16, ok ? src : p.a, ok ? 16u : 0u);
+            const bool ok = kok && (i * (NTC / 8) < rows_left);
+            cp_async16(dst + i * NTC * 16, ok ? src : p.a, ok ? 16u : 0u);
             src += piece_stride;
         }
         if (++i_c == n_chunks) { i_c = 0; ++i_tl; }
@@ -270,7 +269,7 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
     // ---- resident B operand (converter threads): hi/lo panels of W
     if (!is_issuer) {
         if (!BWD) {
-            for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
+            for (int e = tid; e < p.n_pad * p.kred_pad; e += NTC) {
                 const int nn = e / p.kred_pad, r = e - nn * p.kred_pad;
                 float v = 0.0f;
                 if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)nn * p.k + r);
@@ -280,9 +279,9 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
                 *reinterpret_cast<float*>(b_hi + off) = hi;
                 *reinterpret_cast<float*>(b_lo + off) = lo;
             }
-            for (int e = tid; e < 256; e += NT) bias_s[e] = (p.bias && e < p.ncols) ? __ldg(p.bias + e) : 0.0f;
+            for (int e = tid; e < 256; e += NTC) bias_s[e] = (p.bias && e < p.ncols) ? __ldg(p.bias + e) : 0.0f;
         } else {
-            for (int e = tid; e < p.n_pad * p.kred_pad; e += NT) {
+            for (int e = tid; e < p.n_pad * p.kred_pad; e += NTC) {
                 const int r = e / p.n_pad, nn = e - r * p.n_pad;
                 float v = 0.0f;
                 if (r < p.kred && nn < p.ncols) v = __ldg(p.w + (int64_t)r * p.k + nn);
@@ -369,10 +368,10 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
             const bool tail = k0 + CHUNK > p.kred;
 #pragma unroll
             for (int i = 0; i < PIECES; ++i) {
-                const int r = i * (NT / 8) + my_r;
+                const int r = i * (NTC / 8) + my_r;
                 float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 if (p.use_async) {
-                    const float4 t = *reinterpret_cast<const float4*>(rs + i * NT * 16);
+                    const float4 t = *reinterpret_cast<const float4*>(rs + i * NTC * 16);
                     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
                     if (tail) {
 #pragma unroll
@@ -416,7 +415,7 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
             const int my_row = tid & 127;
             for (int cb = 0; cb < p.n_pad; cb += 64) {
                 const int cw = min(64, p.n_pad - cb);
-                for (int c0 = (warp >> 2) * 16; c0 < cw; c0 += 32) {
+                for (int c0 = (warp >> 2) * 16; c0 < cw; c0 += (NTC / 128) * 16) {
                     uint32_t r0[16], r1[16];
                     tmem_ld16(lane_addr + (uint32_t)(cb + c0), r0);
                     tmem_ld16(lane_addr + (uint32_t)(p.n_pad + cb + c0), r1);
@@ -443,10 +442,10 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
                     tc_fence_before();
                     mbar_arrive(accfree_bar);
                 }
-                conv_sync();
+                conv_sync<NTC>();
                 // copy-out: consecutive threads write consecutive 16-byte pieces of a row
                 const int q_per_row = cw / 4;                  // 4, 8, 12 or 16
-                const int rows_per_pass = NT / q_per_row;      // exact for 4, 8, 16; 12 -> 21 rows (+4 idle threads)
+                const int rows_per_pass = NTC / q_per_row;      // exact for 4, 8, 16; 12 -> 21 rows (+4 idle threads)
                 const int q = tid % q_per_row, r_first = tid / q_per_row;
                 if (r_first < rows_per_pass) {
                     for (int r = r_first; r < ROWS; r += rows_per_pass) {
@@ -488,7 +487,7 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
                         }
                     }
                 }
-                conv_sync();         // staging buffer free (next column block / next tile's operands)
+                conv_sync<NTC>();         // staging buffer free (next column block / next tile's operands)
             }
         }
         if (p.use_async) cp_async_wait<0>();
@@ -500,19 +499,27 @@ __global__ void __launch_bounds__(NT_ALL) tc_linear_kernel(const Params p) {
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-template <bool BWD, int ACT>
+template <bool BWD, int ACT, int NTC>
 static int launch_t(Params& p, size_t smem, int64_t grid, cudaStream_t st, const char* what) {
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BWD, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BWD, ACT, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("%s: cudaFuncSetAttribute(%zu): %s", what, smem, cudaGetErrorString(e));
             return -2;
         }
         configured = smem;
     }
-    tc_linear_kernel<BWD, ACT><<<(unsigned)grid, NT_ALL, smem, st>>>(p);
+    tc_linear_kernel<BWD, ACT, NTC><<<(unsigned)grid, NTC + 32, smem, st>>>(p);
     return check_launch(what);
+}
+
+// One CTA per SM (wide layers: the resident weight panels fill shared memory) runs 16 converter warps, the
+// 2-3 CTA configurations 8 each: either way ~16+ warps per SM hide the converters' fixed-latency chains.
+template <bool BWD, int ACT>
+static int launch_w(Params& p, size_t smem, int64_t grid, int ctas_per_sm, cudaStream_t st, const char* what) {
+    if (ctas_per_sm == 1) return launch_t<BWD, ACT, 512>(p, smem, grid, st, what);
+    return launch_t<BWD, ACT, NT>(p, smem, grid, st, what);
 }
 
 template <bool BWD>
@@ -564,10 +571,10 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
     const int64_t n_tiles = ceil_div(p.n, ROWS);
     int64_t grid = 148 * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (BWD) return launch_t<true, 0>(p, smem, grid, st, what);
-    if (p.act == EMER_ACT_RELU) return launch_t<false, EMER_ACT_RELU>(p, smem, grid, st, what);
-    if (p.act == EMER_ACT_SIGMOID) return launch_t<false, EMER_ACT_SIGMOID>(p, smem, grid, st, what);
-    return launch_t<false, EMER_ACT_NONE>(p, smem, grid, st, what);
+    if (BWD) return launch_w<true, 0>(p, smem, grid, ctas_per_sm, st, what);
+    if (p.act == EMER_ACT_RELU) return launch_w<false, EMER_ACT_RELU>(p, smem, grid, ctas_per_sm, st, what);
+    if (p.act == EMER_ACT_SIGMOID) return launch_w<false, EMER_ACT_SIGMOID>(p, smem, grid, ctas_per_sm, st, what);
+    return launch_w<false, EMER_ACT_NONE>(p, smem, grid, ctas_per_sm, st, what);
 }
 
 }  // namespace tc
@@ -607,8 +614,19 @@ struct WParams {
     int tmem_cols;
 };
 
-// 8 converter warps + 1 MMA-issuing warp, mbarrier ring between them (see tc_linear_kernel).
-__global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
+// 16 converter warps + 1 MMA-issuing warp, mbarrier ring between them (see tc_linear_kernel).  One CTA per SM
+// (the operand buffers fill shared memory), so the converter warps are the only latency hiding there is:
+// the ncu capture of the 8-warp version (profiles/r1_prof_wgrad_summary.md) sat at 2.2 warps per scheduler,
+// 42 % issue-active, stalled on fixed-latency dependencies (`wait`) -- hence 16 warps, and item indices
+// advanced incrementally instead of by integer division.
+constexpr int WNT = 512;
+constexpr int WNT_ALL = WNT + 32;
+
+__device__ __forceinline__ void wconv_sync() {       // barrier among the converter threads only
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(WNT_ALL) tc_wgrad_kernel(const WParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int RQn = p.w_rows / 4;
     const int a_panel = p.a_rows * 16 + 16;
@@ -628,10 +646,10 @@ __global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const bool is_issuer = warp == NT / 32;
+    const bool is_issuer = warp == WNT / 32;
     if (tid == 0) {
-        mbar_init(&full_bar[0], NT);
-        mbar_init(&full_bar[1], NT);
+        mbar_init(&full_bar[0], WNT);
+        mbar_init(&full_bar[1], WNT);
         mbar_init(&empty_bar[0], 1);
         mbar_init(&empty_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -641,28 +659,42 @@ __global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     }
     // operand buffers start as zeros: padding features / columns never hold NaN bit patterns
-    for (int i = tid * 16; i < p.nbuf * buf_bytes; i += NT_ALL * 16)
+    for (int i = tid * 16; i < p.nbuf * buf_bytes; i += WNT_ALL * 16)
         *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const int64_t n_tiles = (p.n + p.w_rows - 1) / p.w_rows;
     const int my_tiles = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int xq = p.k_pad4 / 4, zq = p.n_pad / 4;
 
+    // Work items e = tid, tid + WNT, ... of a [major, minor] index space: (e / width, e % width) advanced by
+    // (WNT / width, WNT % width) with one carry -- the divisions happen once per kernel, not once per item.
+    struct Walk { int maj0, min0, dmaj, dmin; };
+    auto walk = [&](int width) { return Walk{tid / width, tid % width, WNT / width, WNT % width}; };
+    const Walk w_xq = walk(xq), w_zq = walk(zq), w_a = walk(p.k_pad4), w_b = walk(p.n_pad);
+
     auto issue = [&](int t) {             // converter threads only
         const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * p.w_rows;
         uint8_t* dx = raw + (t % p.raw_stages) * raw_stage;
         uint8_t* dzs = dx + rawx_bytes;
-        for (int e = tid; e < p.w_rows * xq; e += NT) {
-            const int r = e / xq, q = e - r * xq;
-            const int64_t row = row0 + r;
-            const bool ok = (row < p.n) && (q * 4 < p.k);
-            cp_async16(dx + e * 16, ok ? (p.x + row * p.ldx + q * 4) : p.x, ok ? 16u : 0u);
+        {
+            int r = w_xq.maj0, q = w_xq.min0;
+            for (int e = tid; e < p.w_rows * xq; e += WNT) {
+                const int64_t row = row0 + r;
+                const bool ok = (row < p.n) && (q * 4 < p.k);
+                cp_async16(dx + e * 16, ok ? (p.x + row * p.ldx + q * 4) : p.x, ok ? 16u : 0u);
+                r += w_xq.dmaj; q += w_xq.dmin;
+                if (q >= xq) { q -= xq; ++r; }
+            }
         }
-        for (int e = tid; e < p.w_rows * zq; e += NT) {
-            const int r = e / zq, q = e - r * zq;
-            const int64_t row = row0 + r;
-            const bool ok = (row < p.n) && (q * 4 < p.n_out);
-            cp_async16(dzs + e * 16, ok ? (p.dz + row * p.lddz + q * 4) : p.dz, ok ? 16u : 0u);
+        {
+            int r = w_zq.maj0, q = w_zq.min0;
+            for (int e = tid; e < p.w_rows * zq; e += WNT) {
+                const int64_t row = row0 + r;
+                const bool ok = (row < p.n) && (q * 4 < p.n_out);
+                cp_async16(dzs + e * 16, ok ? (p.dz + row * p.lddz + q * 4) : p.dz, ok ? 16u : 0u);
+                r += w_zq.dmaj; q += w_zq.dmin;
+                if (q >= zq) { q -= zq; ++r; }
+            }
         }
     };
     if (!is_issuer) {
@@ -710,14 +742,17 @@ __global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
             ++use[b];
         }
     } else {
-        float bsum = 0.0f;        // thread t < n_out owns db[t]
+        // db: with n_pad | WNT every thread meets one dZ column only (o = tid % n_pad) and keeps its partial column
+        // sum in a register; otherwise threads 0..n_out-1 walk the raw tile (the old, slower way)
+        const bool bias_in_loop = p.db && (WNT % p.n_pad == 0);
+        float bsum = 0.0f;
         uint32_t use[2] = {0, 0};
         for (int t = 0; t < my_tiles; ++t) {
             const int b = (p.nbuf == 2) ? (t & 1) : 0;
             // raw tile t landed (each thread waits for its own pieces; the barrier publishes all of them)
             if (p.raw_stages == 2) cp_async_wait<1>();
             else cp_async_wait<0>();
-            conv_sync();
+            wconv_sync();
             if (use[b] > 0) mbar_wait(&empty_bar[b], (use[b] - 1) & 1);     // MMAs that read buffer b retired
             uint8_t* a_hi = ops + b * buf_bytes;
             uint8_t* a_lo = a_hi + a_bytes;
@@ -726,59 +761,70 @@ __global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
             const float* rx = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage);
             const float* rz = reinterpret_cast<const float*>(raw + (t % p.raw_stages) * raw_stage + rawx_bytes);
             // ---- A = X^T: item (rq, f): rows 4rq..4rq+3 of feature f -> one 16-byte k group
-            for (int e = tid; e < RQn * p.k_pad4; e += NT) {
-                const int rq = e / p.k_pad4, f = e - rq * p.k_pad4;
-                float4 h, l;
-                if (f < p.k) {
-                    const float* src = rx + (rq * 4) * p.k_pad4 + f;
-                    split(src[0], h.x, l.x);
-                    split(src[p.k_pad4], h.y, l.y);
-                    split(src[2 * p.k_pad4], h.z, l.z);
-                    split(src[3 * p.k_pad4], h.w, l.w);
-                } else {
-                    h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                int rq = w_a.maj0, f = w_a.min0;
+                for (int e = tid; e < RQn * p.k_pad4; e += WNT) {
+                    float4 h, l;
+                    if (f < p.k) {
+                        const float* src = rx + (rq * 4) * p.k_pad4 + f;
+                        split(src[0], h.x, l.x);
+                        split(src[p.k_pad4], h.y, l.y);
+                        split(src[2 * p.k_pad4], h.z, l.z);
+                        split(src[3 * p.k_pad4], h.w, l.w);
+                    } else {
+                        h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const int off = (p.a_rows == 128) ? ((f >> 7) * RQn + rq) * a_panel + (f & 127) * 16
+                                                      : rq * a_panel + f * 16;
+                    *reinterpret_cast<float4*>(a_hi + off) = h;
+                    *reinterpret_cast<float4*>(a_lo + off) = l;
+                    rq += w_a.dmaj; f += w_a.dmin;
+                    if (f >= p.k_pad4) { f -= p.k_pad4; ++rq; }
                 }
-                const int off = (p.a_rows == 128) ? ((f >> 7) * RQn + rq) * a_panel + (f & 127) * 16
-                                                  : rq * a_panel + f * 16;
-                *reinterpret_cast<float4*>(a_hi + off) = h;
-                *reinterpret_cast<float4*>(a_lo + off) = l;
             }
             // ---- B = dZ^T
-            for (int e = tid; e < RQn * p.n_pad; e += NT) {
-                const int rq = e / p.n_pad, o = e - rq * p.n_pad;
-                float4 h, l;
-                if (o < p.n_out) {
-                    const float* src = rz + (rq * 4) * p.n_pad + o;
-                    split(src[0], h.x, l.x);
-                    split(src[p.n_pad], h.y, l.y);
-                    split(src[2 * p.n_pad], h.z, l.z);
-                    split(src[3 * p.n_pad], h.w, l.w);
-                } else {
-                    h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                int rq = w_b.maj0, o = w_b.min0;
+                for (int e = tid; e < RQn * p.n_pad; e += WNT) {
+                    float4 h, l;
+                    if (o < p.n_out) {
+                        const float* src = rz + (rq * 4) * p.n_pad + o;
+                        const float v0 = src[0], v1 = src[p.n_pad], v2 = src[2 * p.n_pad], v3 = src[3 * p.n_pad];
+                        if (bias_in_loop) bsum += (v0 + v1) + (v2 + v3);
+                        split(v0, h.x, l.x);
+                        split(v1, h.y, l.y);
+                        split(v2, h.z, l.z);
+                        split(v3, h.w, l.w);
+                    } else {
+                        h = l = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(b_hi + rq * b_panel + o * 16) = h;
+                    *reinterpret_cast<float4*>(b_lo + rq * b_panel + o * 16) = l;
+                    rq += w_b.dmaj; o += w_b.dmin;
+                    if (o >= p.n_pad) { o -= p.n_pad; ++rq; }
                 }
-                *reinterpret_cast<float4*>(b_hi + rq * b_panel + o * 16) = h;
-                *reinterpret_cast<float4*>(b_lo + rq * b_panel + o * 16) = l;
             }
-            if (p.db && tid < p.n_out) {
+            if (p.db && !bias_in_loop && tid < p.n_out) {
                 for (int r = 0; r < p.w_rows; ++r) bsum += rz[r * p.n_pad + tid];
             }
             fence_async_proxy();
             mbar_arrive(&full_bar[b]);
             ++use[b];
-            conv_sync();                        // everyone is done reading raw stage t
+            wconv_sync();                       // everyone is done reading raw stage t
             if (t + p.raw_stages < my_tiles) issue(t + p.raw_stages);
             cp_async_commit();
         }
+        cp_async_wait<0>();
         if (my_tiles > 0) {
             const int lb = (p.nbuf == 2) ? ((my_tiles - 1) & 1) : 0;
             mbar_wait(&empty_bar[lb], (use[lb] - 1) & 1);          // the last tile's MMAs retired
             if (p.nbuf == 2 && my_tiles > 1) mbar_wait(&empty_bar[lb ^ 1], (use[lb ^ 1] - 1) & 1);
             tc_fence_after();
-            // flush: lane f of block mb holds dW^T[mb*128 + f, :]
+            // flush: lane f of block mb holds dW^T[mb*128 + f, :]; warps w, w+4, w+8, w+12 share lane quadrant w
             for (int mb = 0; mb < p.m_blocks; ++mb) {
                 const int f = mb * 128 + (tid & 127);
                 const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mb * 2 * p.n_pad);
-                for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += 32) {
+                for (int c0 = (warp >> 2) * 16; c0 < p.n_pad; c0 += (WNT / 128) * 16) {
                     uint32_t r0[16], r1[16];
                     tmem_ld16(lane_addr + (uint32_t)c0, r0);
                     tmem_ld16(lane_addr + (uint32_t)(p.n_pad + c0), r1);
@@ -793,9 +839,20 @@ __global__ void __launch_bounds__(NT_ALL) tc_wgrad_kernel(const WParams p) {
                     }
                 }
             }
-            if (p.db && tid < p.n_out) atomicAdd(p.db + tid, bsum);
+            if (bias_in_loop) {
+                // fold the WNT / n_pad partial sums of every column in shared memory (the raw ring is idle now)
+                float* red = reinterpret_cast<float*>(raw);
+                red[tid] = bsum;
+                wconv_sync();
+                if (tid < p.n_out) {
+                    float acc = 0.0f;
+                    for (int j = tid; j < WNT; j += p.n_pad) acc += red[j];
+                    atomicAdd(p.db + tid, acc);
+                }
+            } else if (p.db && tid < p.n_out) {
+                atomicAdd(p.db + tid, bsum);
+            }
         }
-        cp_async_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -881,6 +938,6 @@ extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const floa
     const int64_t n_tiles = emer::ceil_div(n, p.w_rows);
     int64_t grid = 148;
     if (grid > n_tiles) grid = n_tiles;
-    tc_wgrad_kernel<<<(unsigned)grid, NT_ALL, smem, (cudaStream_t)stream>>>(p);
+    tc_wgrad_kernel<<<(unsigned)grid, WNT_ALL, smem, (cudaStream_t)stream>>>(p);
     return emer::check_launch("emer_linear_tc_bwd_weight");
 }
