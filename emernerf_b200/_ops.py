@@ -269,13 +269,13 @@ class _MLPChain(torch.autograd.Function):
         L = len(ws)
         inputs, lds, outs = [], [], []
         cur, ld = x2, ldx
-        shared = False           # x already sits behind the hidden columns of the caller's concat buffer
+        cat = None               # [n, pad4(h + k0)] buffer of the skip concatenation [hidden | x]
+        shared = False           # ... which is the caller's: x already sits behind the hidden columns
         for i, (w, b) in enumerate(zip(ws, bs)):
             n_out, k = w.shape
             if i == skip_layer and i > 0:
-                # cur is cat[:, :h] (written by layer i-1); the chain input goes behind it
+                # layer i-1 wrote cat[:, :h]; the chain input goes behind it
                 h = ws[i - 1].shape[0]
-                cat = cur._base if cur._base is not None else cur
                 if not shared:
                     cat[:, h:h + k0].copy_(x2)
                 cur, ld = cat[:, :h + k0], cat.shape[1]
@@ -287,12 +287,12 @@ class _MLPChain(torch.autograd.Function):
                           and catbuf.dtype == torch.float32 and tuple(catbuf.shape) == (n, _pad4(n_out + k0))
                           and x2.data_ptr() == catbuf.data_ptr() + 4 * n_out and ldx == catbuf.shape[1])
                 if shared:
-                    buf = catbuf
+                    cat = catbuf
                 else:
-                    buf = torch.empty((n, _pad4(n_out + k0)), dtype=torch.float32, device=dev)
-                    if buf.shape[1] > n_out + k0:
-                        buf[:, n_out + k0:].zero_()
-                y, ldy = buf[:, :n_out], buf.shape[1]
+                    cat = torch.empty((n, _pad4(n_out + k0)), dtype=torch.float32, device=dev)
+                    if cat.shape[1] > n_out + k0:
+                        cat[:, n_out + k0:].zero_()
+                y, ldy = cat[:, :n_out], cat.shape[1]
             else:
                 y = torch.empty((n, n_out), dtype=torch.float32, device=dev)
                 ldy = n_out
