@@ -398,11 +398,8 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic Waymo-shape rays (3 cams, 640x960, 200 timesteps), random-init MLPs, N(0,0.3) tables",
-        "config": {"workload": f"BASELINE configs[{['static', 'dynamic', 'flow', 'flow_feat'].index(args.variant) + 1}]: "
-                               f"default_config {args.variant} field, {args.rays} rays x {args.samples} samples "
-                               f"per GPU, proposal samples [128, 64], fwd+bwd+Adam, proposal update every ~6th step",
-                   "rays_per_gpu": args.rays, "samples": args.samples, "parallelism": f"ray-sharded dp{world}",
-                   "l2": "no explicit flush: each step streams > 1 GB of tables+activations through the 126 MB L2"},
+        "config": dict(workload_config(args, world),
+                       l2="no explicit flush: each step streams > 1 GB of tables+activations through the 126 MB L2"),
         "gpu_launches": launches,
         "dominant_kernel": {"name": f"{dom[0]}[{dom[1]}]", "share_of_library_kernel_time": by_name[dom] / tot_ms,
                             "avg_launch_ms": dom_ms},
@@ -424,6 +421,14 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------- the CPU arm
+def workload_config(args, world):
+    """The ``config`` both arms report: BASELINE.json's configuration the metric is quoted on."""
+    return {"workload": f"BASELINE configs[{['static', 'dynamic', 'flow', 'flow_feat'].index(args.variant) + 1}]: "
+                        f"default_config {args.variant} field, {args.rays} rays x {args.samples} samples "
+                        f"per GPU, proposal samples [128, 64], fwd+bwd+Adam, proposal update every ~6th step",
+            "rays_per_gpu": args.rays, "samples": args.samples, "parallelism": f"ray-sharded dp{world}"}
+
+
 def cpu_baseline(args, steps, warmup):
     """The oracle (CPU restatement of the reference's Python + tcnn/nerfacc stand-ins) run as a training
     step on the host cores: same config and tables, a bounded sample of ``--cpu-rays`` rays."""
@@ -467,13 +472,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cb = cpu_baseline(args, steps=max(1, min(args.steps, 4)), warmup=max(1, min(args.warmup, 1)))
+    # every step is a bounded sample (--cpu-rays rays) of the workload; at most 16 of them are timed so that the
+    # arm ends within a few minutes whatever K the caller asks for -- "steps" reports what was actually timed
+    steps, warmup = max(1, min(args.steps, 16)), max(1, min(args.warmup, 2))
+    cb = cpu_baseline(args, steps=steps, warmup=warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic Waymo-shape rays",
-        "config": {"workload": f"default_config {args.variant} field, CPU oracle (reference Python restated; "
-                               f"tcnn/nerfacc restated), bounded sample of {args.cpu_rays} rays x {args.samples}"},
+        "steps": steps, "warmup": warmup, "steps_requested": args.steps, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic Waymo-shape rays (3 cams, 640x960, 200 timesteps), random-init MLPs, N(0,0.3) tables",
+        "config": dict(workload_config(args, max(1, args.gpus)),
+                       sample=f"CPU oracle (the reference's Python restated; tcnn / nerfacc restated) on "
+                              f"{args.cpu_rays} rays x {args.samples} samples per step, fwd+bwd, no optimizer step"),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
