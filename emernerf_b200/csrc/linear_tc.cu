@@ -189,6 +189,32 @@ struct Params {
 // on the converters' critical path.  a_stages / raw_stages / ring_bytes are picked by the host so that
 // 2-3 CTAs share an SM whenever shared memory allows.
 
+// The lane of the issuer warp that issues the tcgen05.mma / tcgen05.commit instructions.
+//   0 (this round's measured build): lane 0 by thread index.  The compiler cannot prove that a single lane is
+//     active, so every descriptor is treated as possibly divergent and each tcgen05.mma is wrapped in an
+//     ELECT / 4x R2UR.BROADCAST / BRA.U.ANY waterfall loop (cuobjdump -sass; profiles/r1_sass_mma_issue.md) --
+//     the ~100-165 cycles per issued MMA measured with tools/tc_probe.cu.
+//   1: elect.sync (what CUTLASS's elect_one_sync does): the descriptors live in uniform registers and the UTCHMMA
+//     are issued back to back (same SASS check).  Compiled and inspected, NOT yet run on hardware (the round's GPU
+//     budget was spent when the waterfall was found), hence off by default:  EMER_TC_ELECT_ONE=1 python -m
+//     emernerf_b200.build   turns it on for the A/B measurement.
+#ifndef EMER_TC_ELECT_ONE
+#define EMER_TC_ELECT_ONE 0
+#endif
+__device__ __forceinline__ bool mma_issue_lane(int tid) {
+#if EMER_TC_ELECT_ONE
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+#else
+    return (tid & 31) == 0;
+#endif
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -315,7 +341,7 @@ __global__ void __launch_bounds__(NTC + 32) tc_linear_kernel(const Params p) {
             mbar_wait(&full_bar[s], uses & 1);                       // operands of chunk g are in place
             if (c == 0 && tl > 0) mbar_wait(accfree_bar, (tl - 1) & 1);   // previous tile's accumulators drained
             tc_fence_after();
-            if ((tid & 31) == 0) {
+            if (mma_issue_lane(tid)) {
                 const int k0 = c * CHUNK;
                 const int ksteps = min(CHUNK, p.kred_pad - k0) / 8;
                 const uint32_t a_hi_addr = a_ring_addr + (uint32_t)((s * 2) * A_STAGE >> 4);
@@ -717,7 +743,7 @@ __global__ void __launch_bounds__(WNT_ALL) tc_wgrad_kernel(const WParams p) {
             const int b = (p.nbuf == 2) ? (t & 1) : 0;
             mbar_wait(&full_bar[b], use[b] & 1);
             tc_fence_after();
-            if ((tid & 31) == 0) {
+            if (mma_issue_lane(tid)) {
                 const uint32_t base = smem_u32(ops + b * buf_bytes);
                 const uint32_t a_hi_addr = base >> 4, a_lo_addr = (base + a_bytes) >> 4;
                 const uint32_t b_hi_addr = (base + 2 * a_bytes) >> 4, b_lo_addr = (base + 2 * a_bytes + b_bytes) >> 4;
