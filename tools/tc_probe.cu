@@ -2,6 +2,7 @@
 // with exactly-representable inputs for several (smem layout, descriptor, major-ness) variants and
 // reports which ones reproduce D = A * B^T.  Used to pin the MN-major (transposed-operand) layout
 // of the weight-gradient kernel.   nvcc -gencode arch=compute_100a,code=sm_100a -o tc_probe tc_probe.cu
+// Add -DPROBE_ELECT=1 to issue the MMAs from an elect.sync lane (cycles per MMA without the waterfall loops).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -41,6 +42,21 @@ struct Variant {
 
 // chunk layout, element (r = row in MN, k): (k/4)*panel + r*16 + (k%4)*4      [K-major use]
 // same memory viewed MN-major: element (mn = f, k = r): (f/4)*panel + r*16 + (f%4)*4
+// The MMA-issuing lane.  PROBE_ELECT=0: thread 0 by index (the compiler then wraps every tcgen05.mma in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop -- the 100-165 cycles per MMA first measured with this probe
+// are that loop, see profiles/r1_sass_mma_issue.md).  PROBE_ELECT=1: elect.sync, descriptors in uniform registers.
+#ifndef PROBE_ELECT
+#define PROBE_ELECT 0
+#endif
+__device__ __forceinline__ bool issue_lane(int tid) {
+#if PROBE_ELECT
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+#else
+    return tid == 0;
+#endif
+}
 __global__ void probe(const Variant v, float* out, int a_panel, int b_panel, int K, long long* cycles, int reps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -85,7 +101,7 @@ __global__ void probe(const Variant v, float* out, int a_panel, int b_panel, int
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    if (tid == 0) {
+    if (warp == 0 && issue_lane(tid)) {
         uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
         idesc |= (uint32_t)v.a_major << 15;
         idesc |= (uint32_t)v.b_major << 16;
