@@ -37,6 +37,12 @@ def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+def on_device(t: Tensor) -> bool:
+    """Whether ``t`` lives where the kernels run.  The fused-path selectors ask through this one predicate (the
+    CPU harness of tests/cabi_emulator.py answers for them; the product has no CPU path, see _need_cuda)."""
+    return t.is_cuda
+
+
 def _need_cuda(*ts: Tensor) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:

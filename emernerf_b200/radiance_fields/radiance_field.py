@@ -195,7 +195,7 @@ class RadianceField(nn.Module):
         """(dirs [R,3], idx [R] | None, emb weight | None) when the fused tail applies: default density
         activation, per-ray view directions / embedding indices handed over as stride-0 per-sample views
         (what render_rays builds), CUDA tensors.  None -> the general per-point path."""
-        if not (self._fused_density and directions is not None and directions.is_cuda and directions.dim() == 3
+        if not (self._fused_density and directions is not None and _ops.on_device(directions) and directions.dim() == 3
                 and directions.stride(1) == 0):
             return None
         idx = emb = None
