@@ -196,8 +196,42 @@ def _pad4(v: int) -> int:
     return (v + 3) // 4 * 4
 
 
-def _tc_rows_ok(n: int, k: int, n_out: int) -> bool:
-    return LINEAR_IMPL == "tc" and n >= TC_MIN_ROWS and k <= 256 and n_out <= 256
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+_SMEM_MAX = 227 * 1024
+
+
+def _tc_fits(kred: int, ncols: int) -> bool:
+    """Whether tc_linear_kernel can take a layer with reduction width ``kred`` and output width ``ncols``
+    (csrc/linear_tc.cu, launch<>): one MMA spans the padded output width, and the resident hi/lo weight panels
+    plus the smallest operand ring must fit shared memory.  Wider layers run on the CUDA-core kernels."""
+    n_pad, kred_pad = _round_up(ncols, 16), _round_up(kred, 8)
+    w_bytes = 2 * (kred_pad // 4) * n_pad * 16
+    return n_pad <= 256 and w_bytes + 128 * 68 * 4 + (256 * 4 + 6 * 8 + 16) <= _SMEM_MAX
+
+
+def _tc_wgrad_fits(k: int, n_out: int) -> bool:
+    """Same for tc_wgrad_kernel (emer_linear_tc_bwd_weight): TMEM columns for dW^T and one of its tile configurations
+    in shared memory."""
+    if n_out > 128 or k > 256:
+        return False
+    k_pad4, n_pad, m_blocks = _round_up(k, 4), _round_up(n_out, 16), (k + 127) // 128
+    if m_blocks * 2 * n_pad > 512:
+        return False
+    a_rows = 64 if k_pad4 <= 64 else 128
+    for w_rows, nbuf, raw_stages in ((64, 2, 2), (64, 2, 1), (32, 2, 2), (32, 2, 1), (64, 1, 2), (64, 1, 1)):
+        rq = w_rows // 4
+        ops1 = 2 * (m_blocks * rq * (a_rows * 16 + 16)) + 2 * (rq * (n_pad * 16 + 16))
+        raw1 = w_rows * (k_pad4 + n_pad) * 4
+        if nbuf * ops1 + raw_stages * raw1 + 4 * 8 + 16 + 2048 <= _SMEM_MAX:
+            return True
+    return False
+
+
+def _tc_rows_ok(n: int) -> bool:
+    return LINEAR_IMPL == "tc" and n >= TC_MIN_ROWS
 
 
 def _aligned(t: Tensor, ld: int) -> bool:
@@ -213,7 +247,7 @@ def _layer_fwd(x2: Tensor, ldx: int, w: Tensor, b: Optional[Tensor], y: Tensor, 
     if _narrow_ok(k, n_out):
         _lib.call("emer_linear_narrow_fwd", _ptr(x2), ldx, _ptr(w), _ptr(b), _ptr(y), ldy, n, k, n_out, act, _stream())
         return
-    name = "emer_linear_tc_fwd" if _tc_rows_ok(n, k, n_out) else "emer_linear_fwd"
+    name = "emer_linear_tc_fwd" if (_tc_rows_ok(n) and _tc_fits(k, n_out)) else "emer_linear_fwd"
     _lib.call(name, _ptr(x2), ldx, _ptr(w), _ptr(b), _ptr(y), ldy, n, k, n_out, act, _stream())
 
 
@@ -224,7 +258,7 @@ def _layer_bwd_data(dz: Tensor, lddz: int, w: Tensor, dx: Tensor, lddx: int, n: 
     if _narrow_ok(k, n_out):
         _lib.call("emer_linear_narrow_bwd_data", _ptr(dz), lddz, _ptr(w), _ptr(dx), lddx, _ptr(relu_src), ld_relu,
                   relu_cols, n, k, n_out, _stream())
-    elif _tc_rows_ok(n, k, n_out):
+    elif _tc_rows_ok(n) and _tc_fits(n_out, k):
         _lib.call("emer_linear_tc_bwd_data", _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(w), _ptr(dx), lddx,
                   _ptr(relu_src), ld_relu, relu_cols, n, k, n_out, 0, _stream())
     else:
@@ -238,7 +272,7 @@ def _layer_bwd_weight(x2: Tensor, ldx: int, dz: Tensor, lddz: int, w: Tensor, ha
     n_out, k = w.shape
     dw = torch.zeros_like(w)
     db = torch.zeros(n_out, dtype=torch.float32, device=w.device) if has_bias else None
-    tc = (_tc_rows_ok(n, k, n_out) and LINEAR_WGRAD_IMPL == "tc" and n_out <= 128 and n_out % 4 == 0
+    tc = (_tc_rows_ok(n) and LINEAR_WGRAD_IMPL == "tc" and _tc_wgrad_fits(k, n_out) and n_out % 4 == 0
           and _aligned(x2, ldx) and _aligned(dz, lddz) and _pad4(k) <= ldx)
     if _narrow_ok(k, n_out):
         _lib.call("emer_linear_narrow_bwd_weight", _ptr(x2), ldx, _ptr(dz), lddz, _ptr(dw), _ptr(db), n, k, n_out,
@@ -583,6 +617,9 @@ def composite(t0: Tensor, t1: Tensor, sigma: Tensor, want_cdf: bool = False):
     return _Composite.apply(t0, t1, sigma, want_cdf)
 
 
+ACC_MAX_CHANNELS = 256          # csrc/composite.cu: 32 lanes x ACC_MAX_PER_LANE
+
+
 class _Accumulate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w: Tensor, v: Tensor):
@@ -616,4 +653,8 @@ def accumulate(w: Tensor, v: Tensor) -> Tensor:
         v = v.unsqueeze(-1)
     if v.shape[:2] != w.shape:
         raise ValueError(f"accumulate: weights {tuple(w.shape)} vs values {tuple(v.shape)}")
+    if v.shape[-1] > ACC_MAX_CHANNELS:
+        # one launch handles up to 256 channels (a warp per ray, 8 per lane); wider features go in slices
+        return torch.cat([_Accumulate.apply(w, v[..., c:c + ACC_MAX_CHANNELS])
+                          for c in range(0, v.shape[-1], ACC_MAX_CHANNELS)], dim=-1)
     return _Accumulate.apply(w, v)

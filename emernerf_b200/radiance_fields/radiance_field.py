@@ -196,8 +196,8 @@ class RadianceField(nn.Module):
         activation, per-ray view directions / embedding indices handed over as stride-0 per-sample views
         (what render_rays builds), CUDA tensors.  None -> the general per-point path."""
         if not (self._fused_density and directions is not None and _ops.on_device(directions) and directions.dim() == 3
-                and directions.stride(1) == 0):
-            return None
+                and directions.stride(1) == 0 and self.geometry_feature_dim % 4 == 0):
+            return None                                   # (the fused kernel moves 16-byte pieces of the features)
         idx = emb = None
         if self.enable_cam_embedding or self.enable_img_embedding:
             if "cam_idx" in data_dict and self.enable_cam_embedding:

@@ -29,6 +29,16 @@ def _addr(p):
     return p.value or 0
 
 
+def _require(cond, msg: str) -> None:
+    """The library's EMER_REQUIRE checks, mirrored: a call the .so would refuse must fail here too."""
+    if not cond:
+        raise RuntimeError(f"cabi_emulator (as the library would): {msg}")
+
+
+def _aligned16(*ptrs) -> bool:
+    return all(_addr(p) % 16 == 0 for p in ptrs)
+
+
 def _view(ptr, rows: int, cols: int, ld=None, ctype=ctypes.c_float, dtype=np.float32):
     """[rows, cols] tensor aliasing the caller's memory at ``ptr`` with row stride ``ld`` (elements)."""
     addr = _addr(ptr)
@@ -72,8 +82,17 @@ def _act_grad(g, y, act):
 
 
 # ----------------------------------------------------------------------------- hash grid
+def _check_grid(geom):
+    _require(geom.n_dims in (3, 4) and 1 <= geom.n_levels <= 16 and geom.n_feat in (1, 2, 4), "grid: bad descriptor")
+    for l in range(geom.n_levels):
+        size = geom.offsets[l + 1] - geom.offsets[l]
+        _require(size > 0 and (not geom.hashed[l] or size & (size - 1) == 0), f"grid: level {l} size {size}")
+
+
 def emer_grid_fwd(desc, x, table, y, n, stream):
     geom = _geom(desc)
+    _check_grid(geom)
+    _require(_aligned16(x, table, y), "emer_grid_fwd: pointers must be 16-byte aligned")
     xs = _view(x, n, geom.n_dims)
     tb = _vec(table, geom.n_params)
     with torch.no_grad():
@@ -82,6 +101,8 @@ def emer_grid_fwd(desc, x, table, y, n, stream):
 
 def emer_grid_bwd(desc, x, table, dy, dtable, dx, n, stream):
     geom = _geom(desc)
+    _check_grid(geom)
+    _require(_aligned16(x, table, dy, dtable, dx), "emer_grid_bwd: pointers must be 16-byte aligned")
     xs = _view(x, n, geom.n_dims).clone().requires_grad_(bool(_addr(dx)))
     tb = _vec(table, geom.n_params).clone().requires_grad_(bool(_addr(dtable)))
     g = _view(dy, n, geom.n_output_dims)
@@ -107,6 +128,8 @@ def _contract(pos, aabb, unbounded, apply_selector):
 
 
 def emer_contract_fwd(pos, aabb6, time, out, out_dim, unbounded, apply_selector, n, stream):
+    _require(out_dim in (3, 4) and (out_dim == 3 or _aligned16(out)), "emer_contract_fwd: out_dim / alignment")
+    _require(out_dim == 3 or _addr(time), "emer_contract_fwd: out_dim 4 needs the time column")
     o = _view(out, n, out_dim)
     with torch.no_grad():
         o[:, :3] = _contract(_view(pos, n, 3), _vec(aabb6, 6), unbounded, apply_selector)
@@ -136,6 +159,7 @@ def emer_trunc_exp_bwd(x, ldx, dy, dx, n, stream):
 
 # ----------------------------------------------------------------------------- dense layers
 def emer_linear_fwd(x, ldx, w, b, y, ldy, n, k, n_out, act, stream):
+    _require(k > 0 and n_out > 0 and ldx >= k and ldy >= n_out, f"emer_linear_fwd: bad shape k={k} n_out={n_out}")
     with torch.no_grad():
         v = _view(x, n, k, ldx) @ _view(w, n_out, k).t()
         if _addr(b):
@@ -143,7 +167,30 @@ def emer_linear_fwd(x, ldx, w, b, y, ldy, n, k, n_out, act, stream):
         _view(y, n, n_out, ldy).copy_(_act(v, act))
 
 
-emer_linear_tc_fwd = emer_linear_narrow_fwd = emer_linear_fwd
+def _r(v, m):
+    return (v + m - 1) // m * m
+
+
+def _check_tc(kred, ncols, what):
+    """linear_tc.cu launch<>: one MMA covers the output width; the resident weight panels must fit shared memory."""
+    n_pad, kred_pad = _r(ncols, 16), _r(kred, 8)
+    _require(n_pad <= 256, f"{what}: output width {ncols} exceeds one MMA (256)")
+    smem = 2 * (kred_pad // 4) * n_pad * 16 + 34816 + 256 * 4 + 6 * 8 + 16
+    _require(smem <= 227 * 1024, f"{what}: layer needs {smem} B of shared memory")
+
+
+def _check_narrow(k, n_out, what):
+    _require(1 <= n_out <= 8 and 1 <= k <= 256, f"{what}: k={k} n_out={n_out}")
+
+
+def emer_linear_tc_fwd(x, ldx, w, b, y, ldy, n, k, n_out, act, stream):
+    _check_tc(k, n_out, "emer_linear_tc_fwd")
+    emer_linear_fwd(x, ldx, w, b, y, ldy, n, k, n_out, act, stream)
+
+
+def emer_linear_narrow_fwd(x, ldx, w, b, y, ldy, n, k, n_out, act, stream):
+    _check_narrow(k, n_out, "emer_linear_narrow_fwd")
+    emer_linear_fwd(x, ldx, w, b, y, ldy, n, k, n_out, act, stream)
 
 
 def _bwd_data(dz, w, dx, relu_src, relu_cols, accumulate):
@@ -164,12 +211,14 @@ def emer_linear_bwd_data(dy, lddy, y, ldy, act, w, dx, lddx, n, k, n_out, accumu
 
 def emer_linear_tc_bwd_data(dy, lddy, y, ldy, act, w, dx, lddx, relu_src, ld_relu, relu_cols, n, k, n_out, accumulate,
                             stream):
+    _check_tc(n_out, k, "emer_linear_tc_bwd_data")
     dz = _act_grad(_view(dy, n, n_out, lddy), _view(y, n, n_out, ldy) if act else None, act)
     mask = _view(relu_src, n, relu_cols, ld_relu) if _addr(relu_src) and relu_cols > 0 else None
     _bwd_data(dz, _view(w, n_out, k), _view(dx, n, k, lddx), mask, relu_cols, accumulate)
 
 
 def emer_linear_narrow_bwd_data(dz, lddz, w, dx, lddx, relu_src, ld_relu, relu_cols, n, k, n_out, stream):
+    _check_narrow(k, n_out, "emer_linear_narrow_bwd_data")
     mask = _view(relu_src, n, relu_cols, ld_relu) if _addr(relu_src) and relu_cols > 0 else None
     _bwd_data(_view(dz, n, n_out, lddz), _view(w, n_out, k), _view(dx, n, k, lddx), mask, relu_cols, 0)
 
@@ -186,13 +235,30 @@ def emer_linear_bwd_weight(x, ldx, dy, lddy, y, ldy, act, dw, db, n, k, n_out, s
     _bwd_weight(_view(x, n, k, ldx), dz, _view(dw, n_out, k), _vec(db, n_out))
 
 
+def _check_tc_wgrad(x, ldx, dz, lddz, k, n_out):
+    """emer_linear_tc_bwd_weight's argument checks (linear_tc.cu), restated."""
+    _require(n_out <= 128 and k <= 256, f"emer_linear_tc_bwd_weight: widths k={k} n_out={n_out} out of range")
+    _require(ldx % 4 == 0 and lddz % 4 == 0 and _aligned16(x, dz), "emer_linear_tc_bwd_weight: rows must be 16-byte aligned")
+    _require(_r(k, 4) <= ldx and _r(n_out, 4) <= lddz, "emer_linear_tc_bwd_weight: row stride shorter than the padded width")
+    m_blocks, n_pad, k4 = (k + 127) // 128, _r(n_out, 16), _r(k, 4)
+    _require(m_blocks * 2 * n_pad <= 512, "emer_linear_tc_bwd_weight: accumulator does not fit TMEM")
+    a_panel, b_panel = (64 if k4 <= 64 else 128) * 16 + 16, n_pad * 16 + 16
+    fits = False
+    for rows, nbuf, stages in ((64, 2, 2), (64, 2, 1), (32, 2, 2), (32, 2, 1), (64, 1, 2), (64, 1, 1)):
+        ops = 2 * m_blocks * (rows // 4) * a_panel + 2 * (rows // 4) * b_panel           # hi + lo of A and of B
+        fits = fits or nbuf * ops + stages * rows * (k4 + n_pad) * 4 + 48 + 2048 <= 227 * 1024
+    _require(fits, f"emer_linear_tc_bwd_weight: layer {k}x{n_out} does not fit shared memory")
+
+
 def emer_linear_tc_bwd_weight(x, ldx, dz, lddz, dw, db, n, k, n_out, stream):
-    if ldx % 4 or lddz % 4 or _addr(x) % 16 or _addr(dz) % 16:
-        raise RuntimeError("emer_linear_tc_bwd_weight: rows must be 16-byte aligned")      # as the library
+    if n == 0:
+        return
+    _check_tc_wgrad(x, ldx, dz, lddz, k, n_out)
     _bwd_weight(_view(x, n, k, ldx), _view(dz, n, n_out, lddz), _view(dw, n_out, k), _vec(db, n_out))
 
 
 def emer_linear_narrow_bwd_weight(x, ldx, dz, lddz, dw, db, n, k, n_out, stream):
+    _check_narrow(k, n_out, "emer_linear_narrow_bwd_weight")
     _bwd_weight(_view(x, n, k, ldx), _view(dz, n, n_out, lddz), _view(dw, n_out, k), _vec(db, n_out))
 
 
@@ -217,6 +283,7 @@ def _resample(vals, cdfs, n, bias, s_min, s_max, kind):
 
 
 def emer_pdf_resample(vals, cdfs, m1, n, bias, s_min, s_max, kind, out_s, out_t, out_bins, n_rays, stream):
+    _require(m1 >= 2 and n >= 1 and kind in _S_TO_T, "emer_pdf_resample: need m1 >= 2 edges, n >= 1 intervals, a known warp")
     v, c = _view(vals, n_rays, m1), _view(cdfs, n_rays, m1)
     b = _vec(bias, n_rays)
     with torch.no_grad():
@@ -234,6 +301,9 @@ def emer_prop_level(desc, prev_s, prev_cdf, m1, n, bias, s_min, s_max, kind, ori
                     w0, b0, w1, b1, out_s, out_t, out_cdf, n_rays, stream):
     geom = _geom(desc)
     lf = geom.n_output_dims
+    _check_grid(geom)
+    _require(geom.n_dims == 3 and lf <= 16 and geom.n_feat <= 4, "emer_prop_level: 3-D grids with at most 16 features")
+    _require(m1 >= 2 and n >= 1 and n + 1 <= 257, f"emer_prop_level: n={n} out of range")
     with torch.no_grad():
         s, t = _resample(_view(prev_s, n_rays, m1), _view(prev_cdf, n_rays, m1), n, _vec(bias, n_rays), s_min, s_max,
                          kind)
@@ -257,8 +327,11 @@ def emer_field_tail_fwd(feats, ld_feats, g_dim, dirs, idx, emb, e_dim, out, ld_o
     n = n_rays * n_samples
     width = g_dim + FT_DIR + e_dim
     w4 = (width + 3) // 4 * 4
-    if ld_out % 4 or ld_out < w4 or _addr(out) % 16:
-        raise RuntimeError("emer_field_tail_fwd: output rows must be 16-byte aligned and wide enough")
+    _require(e_dim == 0 or (_addr(idx) and _addr(emb)), "emer_field_tail_fwd: embedding needs indices and a table")
+    _require(ld_out % 4 == 0 and ld_out >= w4 and _aligned16(out),
+             "emer_field_tail_fwd: output rows must be 16-byte aligned and wide enough")
+    _require(g_dim % 4 == 0 and w4 - g_dim <= 72, f"emer_field_tail_fwd: geometry width {g_dim} must be a multiple of 4 "
+             "and the tail at most 72 floats")
     f = _view(feats, n, g_dim, ld_feats)
     o = _view(out, n, w4, ld_out)
     with torch.no_grad():
@@ -276,6 +349,7 @@ def emer_field_tail_fwd(feats, ld_feats, g_dim, dirs, idx, emb, e_dim, out, ld_o
 
 def emer_field_tail_bwd(feats, ld_feats, d_out, ld_out, g_dim, d_sigma, idx, d_emb, e_dim, n_rays, n_samples, stream):
     n = n_rays * n_samples
+    _require(e_dim <= 32, f"emer_field_tail_bwd: embedding width {e_dim} > 32")
     g = _view(d_out, n, g_dim + FT_DIR + e_dim, ld_out)
     with torch.no_grad():
         if _addr(d_sigma):
@@ -297,6 +371,7 @@ def _composite(t0, t1, sigma):
 
 
 def emer_composite_fwd(t0, t1, sigma, weights, trans, opacity, depth, median, cdf, n_rays, n_samples, stream):
+    _require(n_samples >= 1, "emer_composite_fwd: n_samples must be >= 1")
     a, b, s = (_view(p, n_rays, n_samples) for p in (t0, t1, sigma))
     with torch.no_grad():
         w, tr, op, dep, steps = _composite(a, b, s)
@@ -325,7 +400,11 @@ def emer_composite_bwd(t0, t1, sigma, weights, trans, g_w, g_t, g_o, g_d, dsigma
     _view(dsigma, n_rays, n_samples).copy_(gs)
 
 
+ACC_MAX_CHANNELS = 32 * 8          # composite.cu: ACC_MAX_PER_LANE = 8
+
+
 def emer_accumulate_fwd(w, v, out, n_rays, n_samples, c, stream):
+    _require(1 <= c <= ACC_MAX_CHANNELS, f"emer_accumulate_fwd: channels {c} out of range")
     with torch.no_grad():
         ww = _view(w, n_rays, n_samples)
         vv = _view(v, n_rays * n_samples, c).reshape(n_rays, n_samples, c)

@@ -161,3 +161,37 @@ def test_sorted_interp_quad_searchsorted_equals_dense_mask():
             assert torch.allclose(a, b, rtol=0, atol=1e-7)
             # (no gradient check: compute_loss feeds detached tensors, gradients reach the proposal
             #  network only through w_prop)
+
+
+def test_tensor_core_eligibility_mirrors_the_library_limits():
+    """_ops only sends a layer to the tcgen05 kernels when the library can take it (csrc/linear_tc.cu launch<>,
+    emer_linear_tc_bwd_weight); the emulator carries an independent restatement of the same limits, so a
+    disagreement between the two shows up here before it can on the GPU."""
+    import ctypes
+
+    import cabi_emulator as em
+    from emernerf_b200 import _ops
+
+    # the shipped layer shapes all run on the tensor cores
+    for k, n_out in ((40, 64), (64, 64), (64, 128), (113, 64), (177, 64), (49, 64), (32, 64)):
+        assert _ops._tc_fits(k, n_out) and _ops._tc_fits(n_out, k) and _ops._tc_wgrad_fits(k, n_out), (k, n_out)
+    assert _ops._tc_fits(128, 113)                       # stacked skip gradient [dZ0 | dZ1] [W0 ; W1[:, h:]]
+    # layers the resident weight panels / accumulators cannot hold
+    assert not _ops._tc_fits(256, 256) and not _ops._tc_fits(113, 256) and not _ops._tc_fits(64, 384)
+    assert not _ops._tc_wgrad_fits(256, 128) and not _ops._tc_wgrad_fits(64, 256) and not _ops._tc_wgrad_fits(369, 64)
+
+    buf = (ctypes.c_float * 64)()
+    ptr = ctypes.c_void_p((ctypes.addressof(buf) + 15) // 16 * 16)
+    for k in range(8, 400, 24):
+        for n_out in range(8, 400, 24):
+            if _ops._tc_fits(k, n_out):
+                em._check_tc(k, n_out, "fwd")            # raises if the library would refuse
+            else:
+                with pytest.raises(RuntimeError):
+                    em._check_tc(k, n_out, "fwd")
+            try:
+                em._check_tc_wgrad(ptr, _ops._pad4(k), ptr, _ops._pad4(n_out), k, n_out)
+                lib_ok = True
+            except RuntimeError:
+                lib_ok = False
+            assert lib_ok == _ops._tc_wgrad_fits(k, n_out), (k, n_out)

@@ -1,0 +1,35 @@
+"""Constructor options and data-dict shapes beyond the four golden cases: the drop-in (host side on CPU through
+tests/cabi_emulator.py) against the REFERENCE's own classes run live -- build container only (needs
+/root/reference; the script runs in a subprocess because the reference's module names enter sys.modules)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.reference
+def test_option_variants_match_the_live_reference():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "live_reference_variants.py")], capture_output=True, text=True,
+                       cwd=os.path.dirname(HERE), timeout=1500)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("JSON:")][-1]
+    res = json.loads(line[5:])
+    assert len(res) >= 16
+    for name, v in res.items():
+        for key, err in v["errors"].items():
+            # rendered outputs and per-sample extras: same arithmetic on the same host -> rounding level;
+            # gradients: summation order of the scatter / weight-gradient reductions
+            tol = 2e-5 if key.startswith("grad/") or key == "prop_loss" else 2e-6
+            assert err <= tol, (name, key, err)
+    calls = {k: set(v["calls"]) for k, v in res.items()}
+    # the fused tail must step aside where the kernel cannot take the layout ...
+    for name in ("mean_embedding", "odd_geometry_width", "wide_embedding"):
+        assert "emer_field_tail_fwd" not in calls[name], name
+    # ... and be the path everywhere else
+    for name in ("cam_embedding", "no_embedding", "bounded_aabb", "narrow_widths", "wide_heads"):
+        assert "emer_field_tail_fwd" in calls[name], name
+    assert "emer_linear_fwd" in calls["wide_heads"] and "emer_linear_bwd_weight" in calls["wide_heads"]
