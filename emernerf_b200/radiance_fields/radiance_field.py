@@ -345,6 +345,9 @@ class RadianceField(nn.Module):
             if return_density_only:
                 return out
             if tail is not None:
+                # a dynamic field asked for colour without timestamps fails like the reference's query_rgb
+                # (radiance_field.py:651-654)
+                assert self.dynamic_xyz_encoder is None, "Dynamic geometry features are not provided."
                 out["rgb"] = self._rgb_from_tail(rgb_in_static)
             elif directions is not None:
                 out["rgb"] = self.query_rgb(directions, geo, data_dict=data_dict)["rgb"]

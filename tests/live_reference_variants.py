@@ -79,6 +79,10 @@ VARIANTS = {
                    None, {}, {}, "train"),                 # layers the tensor-core kernels cannot hold -> CUDA-core path
     "wide_feature_head": (dict(enable_feature_head=True, feature_mlp_layer_width=256, feature_embedding_dim=384,
                                semantic_feature_dim=32), True, True, "features384", {}, {}, "train"),
+    "dynamic_model_no_time": ({}, True, False, "drop_time", {}, {}, "eval"),      # no timestamps: static branch only
+    "one_proposal": ({}, False, False, None, dict(num_samples_per_prop=[24], n_props=1), {}, "train"),
+    "three_proposals": ({}, False, False, None, dict(num_samples_per_prop=[40, 24, 16], n_props=3), {}, "eval"),
+    "many_samples": ({}, False, False, None, dict(num_samples_per_prop=[300, 280], num_samples=270), {}, "eval"),
     "sampling_lindisp": ({}, False, False, None, dict(sampling_type="lindisp"), {}, "eval"),
     "sampling_uniform": ({}, False, False, None, dict(sampling_type="uniform", far_plane=120.0), {}, "eval"),
     "train_stratified": ({}, True, False, None, {}, {}, "train"),
@@ -146,22 +150,55 @@ def run_variant(name):
         batch["cam_idx"] = batch.pop("img_idx") % cases.N_CAMS
     elif edit == "drop_idx":
         batch.pop("img_idx")
+    elif edit == "drop_time":
+        batch.pop("normed_timestamps")
     cfg = cases.render_cfg()
+    cfg_edit = dict(cfg_edit)
+    n_props = cfg_edit.pop("n_props", None)
+    if "num_samples" in cfg_edit:
+        cfg.nerf.sampling.num_samples = cfg_edit.pop("num_samples")
     for k, v in cfg_edit.items():
         setattr(cfg.nerf.propnet, k, v)
+    if n_props is not None:
+        # the same networks on both sides: drop one, or append a third built like the second
+        if n_props < len(rp):
+            rp, op = rp[:n_props], op[:n_props]
+        while len(rp) < n_props:
+            e = cases.ENC_PROP[-1]
+            extra = []
+            for ns in (REF, OURS):
+                torch.manual_seed(9)
+                p = ns.build_density_field(n_input_dims=3, n_levels=e["n_levels"], max_resolution=e["max_resolution"],
+                                           log2_hashmap_size=e["log2_hashmap_size"],
+                                           n_features_per_level=e["n_features_per_level"], unbounded=True)
+                p.set_aabb(cases.AABB)
+                extra.append(p)
+            randomise(extra[0], [], seed=3)
+            extra[1].load_state_dict(extra[0].state_dict())
+            rp, op = rp + [extra[0]], op + [extra[1]]
     train = mode == "train"
     r_est = RefEstimator(torch.optim.Adam([q for p in rp for q in p.parameters()], lr=0.01), None, **est_kw)
     o_est = PropNetEstimator(torch.optim.Adam([q for p in op for q in p.parameters()], lr=0.01), None, **est_kw)
     for m in (rf, of, r_est, o_est, *rp, *op):
         m.train(train)
     errs = {}
+    failures = []
     with torch.set_grad_enabled(train):
-        torch.manual_seed(77)
-        want = ref_render_rays(rf, r_est, rp, dict(batch), cfg, proposal_requires_grad=train,
-                               return_decomposition=not train)
-        torch.manual_seed(77)
-        got = render_rays(of, o_est, op, dict(batch), cfg, proposal_requires_grad=train,
-                          return_decomposition=not train)
+        for fn, args in ((ref_render_rays, (rf, r_est, rp)), (render_rays, (of, o_est, op))):
+            torch.manual_seed(77)
+            try:
+                failures.append(None)
+                res = fn(*args, dict(batch), cfg, proposal_requires_grad=train, return_decomposition=not train)
+            except (AssertionError, ValueError, KeyError) as e:          # same refusal on both sides is parity too
+                failures[-1] = (type(e).__name__, str(e))
+                res = None
+            if fn is ref_render_rays:
+                want = res
+            else:
+                got = res
+    if failures[0] is not None or failures[1] is not None:
+        assert failures[0] == failures[1], failures
+        return {"raises:" + failures[0][0]: 0.0}
     compare(got, want, errs)
     if train:
         wl = r_est.compute_loss(want["extras"]["trans"], 1024.0)

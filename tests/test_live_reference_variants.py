@@ -18,7 +18,7 @@ def test_option_variants_match_the_live_reference():
     assert r.returncode == 0, r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("JSON:")][-1]
     res = json.loads(line[5:])
-    assert len(res) >= 16
+    assert len(res) >= 20
     for name, v in res.items():
         for key, err in v["errors"].items():
             # rendered outputs and per-sample extras: same arithmetic on the same host -> rounding level;
