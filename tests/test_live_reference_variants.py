@@ -33,3 +33,24 @@ def test_option_variants_match_the_live_reference():
     for name in ("cam_embedding", "no_embedding", "bounded_aabb", "narrow_widths", "wide_heads"):
         assert "emer_field_tail_fwd" in calls[name], name
     assert "emer_linear_fwd" in calls["wide_heads"] and "emer_linear_bwd_weight" in calls["wide_heads"]
+
+
+@pytest.mark.reference
+def test_reference_builders_and_default_config_build_the_dropin(tmp_path):
+    """INTEGRATION.md section 1, executed: the reference's unmodified ``builders.py`` + ``configs/default_config.yaml``
+    (every branch switched on, real table sizes) build the model once from the reference's classes and once, after
+    ``install_dropin()``, from this package; the reference's state-dict loads strictly and the same rays render to the
+    same outputs."""
+    script = os.path.join(HERE, "live_dropin_builders.py")
+    blob = str(tmp_path / "ref.pt")
+    for mode in ("ref", "ours"):
+        r = subprocess.run([sys.executable, script, mode, blob], capture_output=True, text=True, cwd=str(tmp_path),
+                           timeout=1500)
+        assert r.returncode == 0, (mode, r.stderr[-3000:])
+        res = json.loads([l for l in r.stdout.splitlines() if l.startswith("JSON:")][-1][5:])
+        if mode == "ref":
+            assert res["n_params"] > 50_000_000 and "dino_feat" in res["keys"] and "forward_flow" in res["keys"]
+    assert len(res["errors"]) >= 30
+    for k, e in res["errors"].items():
+        assert e <= 2e-6, (k, e)
+    assert {"emer_field_tail_fwd", "emer_prop_level", "emer_grid_fwd", "emer_composite_fwd"} <= set(res["calls"])
