@@ -411,6 +411,7 @@ def run_ours(args):
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, steps=2, warmup=1)
+        line.update(parity_vs_oracle(tr, args))         # second half of BASELINE.json's metric: PSNR vs reference
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
@@ -466,6 +467,47 @@ def cpu_baseline(args, steps, warmup):
     return {"value": args.cpu_rays * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{steps} training steps (fwd+bwd, no optimizer) of {args.cpu_rays} rays x {args.samples} "
                       f"samples, same tables/config, {dt:.1f} s", "ms_per_step": dt / steps * 1e3}
+
+
+def parity_vs_oracle(tr, args):
+    """PSNR (datasets/metrics.py:31-46: -10 log10 mse) and max relative errors of the B200 render against the CPU
+    oracle -- the reference's algorithm -- on the SAME weights (the trainer's, after the timed steps) and the same
+    ``--cpu-rays`` Waymo-shape rays, evaluation mode (deterministic: no jitter, unit temporal-aggregation noise).
+    Part of the cpu_baseline leg: the oracle is the checker here, never the thing measured."""
+    import math
+
+    from emernerf_b200 import synthetic
+    from emernerf_b200.radiance_fields.render_utils import render_rays
+    from oracle import adapters, hotpath
+
+    cfg = tr.cfg
+    feats = args.variant == "flow_feat"
+    b = synthetic.pixel_batch(args.cpu_rays, cfg.data.num_timesteps, 3, seed=4242, features=feats)
+    mods = [tr.field, tr.est] + list(tr.props)
+    [m.eval() for m in mods]
+    with torch.no_grad():
+        got = render_rays(tr.field, tr.est, tr.props, {k: v.to(tr.device) for k, v in b.items()}, cfg)
+    torch.cuda.synchronize()
+    [m.train() for m in mods]
+    fsd = adapters.cpu_state_dict(tr.field)
+    psd = [adapters.cpu_state_dict(p) for p in tr.props]
+    with torch.no_grad():
+        want, _ = hotpath.render_rays(fsd, adapters.spec_from_module(tr.field), psd,
+                                      [adapters.spec_from_module(p) for p in tr.props], b, num_samples=args.samples,
+                                      prop_samples=cfg.nerf.propnet.num_samples_per_prop, near_plane=0.1,
+                                      far_plane=1000.0, training=False)
+
+    def rel(k):
+        a, w = got[k].detach().double().cpu(), want[k].detach().double()
+        return float((a - w).abs().max() / w.abs().max().clamp_min(1e-12))
+
+    mse = float((got["rgb"].double().cpu() - want["rgb"].double()).square().mean())
+    errs = {"rgb": rel("rgb"), "depth": rel("depth"), "opacity": rel("opacity")}
+    if "dino_feat" in want:
+        errs["feature"] = rel("dino_feat")
+    return {"psnr_vs_reference": (999.0 if mse == 0 else -10.0 * math.log10(mse)), "max_rel_err": errs,
+            "parity_sample": f"{args.cpu_rays} rays x {args.samples} samples, eval mode, trainer's weights after the timed "
+                             f"steps; reference = CPU oracle (the reference's Python restated, pinned by tests/golden)"}
 
 
 def run_reference(args):

@@ -58,10 +58,11 @@ def load():
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if not os.path.exists(path):
-        from .build import build_library
+    from .build import build_library
 
-        build_library()
+    # (re)build when the library is missing OR stale: build_library() returns at once when build.stamp matches the
+    # digest of the sources, so an edited .cu / header can never run as an old binary
+    build_library()
     lib = ctypes.CDLL(path)
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
@@ -125,7 +126,22 @@ def algorithmic_bytes(tag: str) -> int:
     return n * (l * (2 ** d) * f * 4 + d * 4 + l * f * 4)
 
 
+# device of the tensors of the op being launched (set by _ops._need_cuda); kernels launch on the CUDA runtime's
+# current device, so a call for tensors elsewhere is wrapped in a device guard
+DEVICE = None
+
+
 def call(name: str, *args) -> None:
+    if DEVICE is not None:
+        import torch
+
+        if DEVICE != torch.cuda.current_device():
+            with torch.cuda.device(DEVICE):
+                return _call(name, *args)
+    return _call(name, *args)
+
+
+def _call(name: str, *args) -> None:
     global LAUNCHES
     lib = load()
     prof = _PROFILE

@@ -30,7 +30,8 @@ STOT_KINDS = {"uniform": 0, "lindisp": 1, "sqrt": 2, "log": 3, "uniform_lindisp"
 
 
 def _stream() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream ON THE DEVICE OF THE OP'S TENSORS (see _need_cuda / _lib.DEVICE)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(_lib.DEVICE).cuda_stream)
 
 
 def _ptr(t: Optional[Tensor]) -> ctypes.c_void_p:
@@ -44,9 +45,21 @@ def on_device(t: Tensor) -> bool:
 
 
 def _need_cuda(*ts: Tensor) -> None:
+    """Every forward op starts here: all tensors on ONE CUDA device, which becomes the device the launch (and its
+    stream lookup) is guarded to -- a model on cuda:1 works while the current device is cuda:0.  (Backward nodes run
+    under autograd's own device guard.)"""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("emernerf_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device.index
+        elif t.device.index != dev:
+            raise RuntimeError(f"emernerf_b200 op got tensors on cuda:{dev} and cuda:{t.device.index}")
+    if dev is not None:
+        _lib.DEVICE = dev
 
 
 def _f32c(t: Tensor) -> Tensor:
@@ -563,10 +576,15 @@ def prop_level(prev_s: Tensor, prev_cdf: Tensor, n: int, bias: Optional[Tensor],
     out_cdf = torch.empty_like(out_s)
     if bias is not None:
         bias = _f32c(bias.reshape(-1))
+    # every converted tensor is bound to a local that outlives the launch: a temporary copy made by _f32c would be
+    # freed (and its block reused by the next temporary) before the kernel is even enqueued
+    o, d, box = _f32c(origins), _f32c(dirs), _f32c(aabb.reshape(-1))
+    tab, w0c, b0c, w1c, b1c = _f32c(table), _f32c(w0), _f32c(b0), _f32c(w1.reshape(-1)), _f32c(b1.reshape(-1))
+    if o.shape != (r, 3) or d.shape != (r, 3):
+        raise ValueError(f"prop_level: origins / dirs must be [{r}, 3], got {tuple(o.shape)} / {tuple(d.shape)}")
     _lib.call("emer_prop_level", ctypes.byref(desc.c), _ptr(prev_s), _ptr(prev_cdf), m1, n, _ptr(bias), float(s_min),
-              float(s_max), STOT_KINDS[kind], _ptr(_f32c(origins)), _ptr(_f32c(dirs)), _ptr(_f32c(aabb.reshape(-1))),
-              int(unbounded), _ptr(_f32c(table)), _ptr(_f32c(w0)), _ptr(_f32c(b0)), _ptr(_f32c(w1.reshape(-1))),
-              _ptr(_f32c(b1.reshape(-1))), _ptr(out_s), _ptr(out_t), _ptr(out_cdf), r, _stream())
+              float(s_max), STOT_KINDS[kind], _ptr(o), _ptr(d), _ptr(box), int(unbounded), _ptr(tab), _ptr(w0c),
+              _ptr(b0c), _ptr(w1c), _ptr(b1c), _ptr(out_s), _ptr(out_t), _ptr(out_cdf), r, _stream())
     return out_s, out_t, out_cdf
 
 

@@ -50,10 +50,10 @@ def _digest() -> str:
     for p in sources() + sorted(
             os.path.join(d, f) for d in (CSRC, os.path.join(ROOT, "include"))
             for f in os.listdir(d) if f.endswith((".h", ".cuh"))):
-        h.update(p.encode())
+        h.update(os.path.relpath(p, ROOT).encode())      # relative: the stamp is valid on any checkout path
         with open(p, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f for f in NVCC_FLAGS if not os.path.isabs(f)).encode())
     return h.hexdigest()
 
 

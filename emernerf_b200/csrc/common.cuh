@@ -12,6 +12,8 @@
 namespace emer {
 
 void set_error(const char* fmt, ...);
+int current_device();   // index of the CUDA runtime's current device (0..63)
+int sm_count();         // multiprocessors of the current device (cached per device)
 
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

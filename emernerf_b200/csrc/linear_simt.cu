@@ -240,7 +240,7 @@ extern "C" int emer_linear_bwd_weight(const float* x, int64_t ldx, const float* 
     EMER_REQUIRE(x && dy && dw, "emer_linear_bwd_weight: NULL pointer");
     EMER_REQUIRE(act == EMER_ACT_NONE || y, "emer_linear_bwd_weight: activation needs the stored output");
     // ~4 CTAs per SM worth of row chunks, at least 256 rows each
-    int64_t chunks = 148 * 4;
+    int64_t chunks = (int64_t)sm_count() * 4;
     int64_t rows = ceil_div(n, chunks);
     rows = ceil_div(rows < 256 ? 256 : rows, WR) * WR;
     chunks = ceil_div(n, rows);
@@ -420,7 +420,7 @@ extern "C" int emer_linear_narrow_bwd_weight(const float* x, int64_t ldx, const 
     if (n == 0) return 0;
     EMER_REQUIRE(x && dz && dw, "emer_linear_narrow_bwd_weight: NULL pointer");
     EMER_REQUIRE(n_out >= 1 && n_out <= NARROW_MAX_OUT && k >= 1 && k <= NARROW_MAX_K, "emer_linear_narrow_bwd_weight: k=%d n_out=%d", k, n_out);
-    int64_t chunks = 148 * 8;
+    int64_t chunks = (int64_t)sm_count() * 8;
     int64_t rows = ceil_div(n, chunks);
     if (rows < 64) rows = 64;
     chunks = ceil_div(n, rows);

@@ -199,7 +199,7 @@ struct Params {
 //     budget was spent when the waterfall was found), hence off by default:  EMER_TC_ELECT_ONE=1 python -m
 //     emernerf_b200.build   turns it on for the A/B measurement.
 #ifndef EMER_TC_ELECT_ONE
-#define EMER_TC_ELECT_ONE 0
+#define EMER_TC_ELECT_ONE 1
 #endif
 __device__ __forceinline__ bool mma_issue_lane(int tid) {
 #if EMER_TC_ELECT_ONE
@@ -527,7 +527,8 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 template <bool BWD, int ACT, int NTC>
 static int launch_t(Params& p, size_t smem, int64_t grid, cudaStream_t st, const char* what) {
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};          // the attribute is per device
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<BWD, ACT, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -595,7 +596,7 @@ static int launch(Params& p, cudaStream_t st, const char* what) {
     // TMEM: co-resident CTAs share 512 columns
     while (ctas_per_sm > 1 && ctas_per_sm * p.tmem_cols > 512) --ctas_per_sm;
     const int64_t n_tiles = ceil_div(p.n, ROWS);
-    int64_t grid = 148 * ctas_per_sm;
+    int64_t grid = (int64_t)sm_count() * ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
     if (BWD) return launch_w<true, 0>(p, smem, grid, ctas_per_sm, st, what);
     if (p.act == EMER_ACT_RELU) return launch_w<false, EMER_ACT_RELU>(p, smem, grid, ctas_per_sm, st, what);
@@ -952,7 +953,8 @@ extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const floa
         }
     }
     EMER_REQUIRE(found, "emer_linear_tc_bwd_weight: layer %dx%d does not fit shared memory", k, n_out);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};          // the attribute is per device
+    size_t& configured = configured_dev[emer::current_device()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -962,7 +964,7 @@ extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const floa
         configured = smem;
     }
     const int64_t n_tiles = emer::ceil_div(n, p.w_rows);
-    int64_t grid = 148;
+    int64_t grid = emer::sm_count();
     if (grid > n_tiles) grid = n_tiles;
     tc_wgrad_kernel<<<(unsigned)grid, WNT_ALL, smem, (cudaStream_t)stream>>>(p);
     return emer::check_launch("emer_linear_tc_bwd_weight");

@@ -381,6 +381,17 @@ def test_fused_proposal_level_vs_oracle(stratified):
     assert rel_err(cdf_got, cdf_want) < 2e-5
     assert torch.equal(cdf_got[:, -1].cpu(), torch.ones(R))
 
+    # the reference's pipeline hands over NON-contiguous origins (broadcast of c2w[:, :3, -1], pixel_source.py:71);
+    # converted copies must outlive the launch (they used to be temporaries whose blocks were reused): slices of an
+    # [R, 6] tensor and fp64 rays give the same result as contiguous fp32 ones
+    od = torch.cat([batch["origins"], batch["viewdirs"]], -1).to(DEV)
+    s2, t2, cdf2 = _ops.prop_level(
+        prev_s.to(DEV), prev_cdf.to(DEV), n, None if jit is None else jit.to(DEV), s_min, s_max, "uniform_lindisp",
+        od[:, :3], od[:, 3:].double(), net.aabb, True, net.xyz_encoder.desc,
+        net.xyz_encoder.tcnn_encoding.params, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias)
+    torch.cuda.synchronize()
+    assert torch.equal(s2, s_got) and torch.equal(t2, t_got) and torch.equal(cdf2, cdf_got)
+
 
 @pytest.mark.parametrize("with_emb,extra,front", [(True, 0, 0), (True, 64, 0), (False, 0, 0), (True, 0, 64),
                                                   (False, 64, 32)])

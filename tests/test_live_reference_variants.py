@@ -54,3 +54,20 @@ def test_reference_builders_and_default_config_build_the_dropin(tmp_path):
     for k, e in res["errors"].items():
         assert e <= 2e-6, (k, e)
     assert {"emer_field_tail_fwd", "emer_prop_level", "emer_grid_fwd", "emer_composite_fwd"} <= set(res["calls"])
+
+
+@pytest.mark.reference
+def test_train_script_import_block_runs_after_install_dropin(tmp_path):
+    """The reference's ``train_emernerf.py`` import block (incl. ``radiance_fields.video_utils`` and ``loss`` ->
+    ``from nerfacc import accumulate_along_rays``) executes unmodified after ``install_dropin()``; overridden names
+    come from this package, everything else from the reference tree."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "live_dropin_imports.py")], capture_output=True, text=True,
+                       cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("JSON:")][-1][5:])
+    for k in ("RadianceField", "DensityField", "render_rays", "PropNetEstimator", "nerfacc"):
+        assert "emernerf_b200" in res[k], (k, res[k])
+    for k in ("render_pixels", "builders", "loss", "feature_extractor"):
+        assert "emernerf_b200" not in res[k], (k, res[k])
+    assert "nerfacc" not in res["stubbed"] and "tinycudann" not in res["stubbed"]
+    assert res["los_err"] < 1e-6
