@@ -8,7 +8,7 @@ tensors must live on a CUDA device -- there is no CPU path.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -540,6 +540,149 @@ def field_tail(feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional
         raise ValueError("field_tail: front must be a multiple of 4 (16-byte aligned rows)")
     sigma, rgb_in, buf = _FieldTail.apply(feats, dirs, idx, emb, g_dim, front)
     return (sigma, rgb_in, buf) if front else (sigma, rgb_in)
+
+
+# ----------------------------------------------------------------------------- fused field chain
+FIELD_CHAIN = os.environ.get("EMER_FIELD_CHAIN", "fused")      # "layers": the per-layer path (A/B and debugging switch)
+CHAIN_K_ENC = (32, 40, 64)
+
+
+def _tc_bwd_data_acc(dz: Tensor, lddz: int, w: Tensor, dx: Tensor, lddx: int, n: int) -> None:
+    """dx[n, k] += dz[n, n_out] @ w on the tensor-core layer kernel (accumulating form)."""
+    n_out, k = w.shape
+    _lib.call("emer_linear_tc_bwd_data", _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(w), _ptr(dx), lddx, None, 0, 0, n, k,
+              n_out, 1, _stream())
+
+
+class _FieldChain(torch.autograd.Function):
+    """enc [N, k_enc] -> (sigma [N], rgb [N, 3], geo [N, 64] | None, sem [N, 64] | None): base MLP, density and the
+    colour head in one kernel (``emer_field_fwd``, csrc/field_fused.cu).  ``ray_bias`` [R, 128] carries the per-ray
+    input columns of the colour head and its first two biases (see :func:`field_chain`).
+
+    Backward: the data gradients walk the chain with the tensor-core layer kernels on the saved activations
+    ([h0 | geo] side by side, so layer 1 of the head is one 64 -> 128 product and the skip gradient accumulates in
+    place); ``d_ray_bias`` is the per-ray sum of the two hidden-layer gradients, which hands the per-ray weight
+    columns, the biases and the embedding their gradients through ordinary autograd."""
+
+    @staticmethod
+    def forward(ctx, enc: Tensor, ray_bias: Tensor, samples: int, want_geo: bool, wb0: Tensor, bb0: Tensor, wb1: Tensor,
+                bb1: Tensor, w0: Tensor, w1: Tensor, w2: Tensor, b2: Tensor):
+        ctx.set_materialize_grads(False)
+        _need_cuda(enc, ray_bias, wb0, wb1, w0, w1, w2)
+        enc2, ld_enc = _rows(enc, enc.shape[-1])
+        n, k_enc = enc2.shape
+        n_feat = wb1.shape[0]
+        n_ray_cols = w0.shape[1] - 64                   # [dir | emb] columns in front of geo (radiance_field.py:647)
+        ws = [_f32c(t) for t in (wb0, bb0, wb1, bb1, w0, w1, w2, b2)]
+        wb0c, bb0c, wb1c, bb1c, w0c, w1c, w2c, b2c = ws
+        rb = _f32c(ray_bias)
+        if rb.shape != ((n + samples - 1) // samples, 128):
+            raise ValueError(f"field_chain: ray_bias {tuple(rb.shape)} for {n} points x {samples} samples per ray")
+        dev = enc.device
+        train = any(ctx.needs_input_grad)          # (False under torch.no_grad(): no saves, inference traffic only)
+        f32 = dict(dtype=torch.float32, device=dev)
+        sigma = torch.empty(n, **f32)
+        rgb = torch.empty((n, 3), **f32)
+        hb = torch.empty((n, 64), **f32) if train else None
+        hg = torch.empty((n, 128), **f32) if (train or want_geo) else None
+        h1 = torch.empty((n, 64), **f32) if train else None
+        sem = torch.empty((n, 64), **f32) if n_feat == 128 else None
+        w0g = w0c[:, n_ray_cols:]
+        w1h, w1g = w1c[:, :64], w1c[:, 64 + n_ray_cols:]
+        _lib.call("emer_field_fwd", _ptr(enc2), ld_enc, k_enc, _ptr(wb0c), _ptr(bb0c), _ptr(wb1c), _ptr(bb1c), n_feat,
+                  _ptr(w0g), w0c.shape[1], _ptr(w1h), _ptr(w1g), w1c.shape[1], _ptr(w2c), _ptr(b2c), _ptr(rb), samples,
+                  _ptr(sigma), _ptr(rgb), _ptr(hb), _ptr(hg), _ptr(h1), _ptr(sem), n, _stream())
+        geo = hg[:, 64:] if want_geo else None
+        if train:
+            ctx.save_for_backward(enc2, hb, hg, h1, rgb, sigma, wb0c, wb1c, w0c, w1c, w2c)
+            ctx.meta = (samples, n_ray_cols, n_feat, enc.shape, ld_enc)
+        return sigma, rgb, geo, sem
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_rgb, d_geo, d_sem):
+        enc2, hb, hg, h1, rgb, sigma, wb0, wb1, w0, w1, w2 = ctx.saved_tensors
+        samples, n_ray_cols, n_feat, enc_shape, ld_enc = ctx.meta
+        n, k_enc = enc2.shape
+        dev = enc2.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        none = (None,) * 12
+        if d_sigma is None and d_rgb is None and d_geo is None and d_sem is None:
+            return none
+        n_rays = (n + samples - 1) // samples
+        # D1 = [dZ0 | dGeo] side by side (row stride 128): the hidden-layer gradient of head layer 0 and the
+        # gradient arriving at the geometry features from both head layers
+        D1 = torch.empty((n, 128), **f32)
+        dw0 = dw1 = dw2 = db2 = d_rb = None
+        if d_rgb is not None:
+            dz2 = _f32c(d_rgb.reshape(n, 3)) * (rgb * (1.0 - rgb))
+            dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n)
+            dz1 = torch.empty((n, 64), **f32)
+            _layer_bwd_data(dz2, 3, w2, dz1, 64, n, h1, 64, 64)                       # relu'(h1) applied
+            w1hg = torch.cat([w1[:, :64], w1[:, 64 + n_ray_cols:]], dim=1)            # [64, 128] = [hidden | geo] columns
+            dw1hg, _ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)
+            _layer_bwd_data(dz1, 64, w1hg, D1, 128, n, hg, 128, 64)                   # [relu'(h0) dH0 | dGeo(layer 1)]
+            w0g = w0[:, n_ray_cols:].contiguous()
+            dz0 = D1[:, :64]
+            dw0g, _ = _layer_bwd_weight(hg[:, 64:], 128, dz0, 128, w0g, False, n)
+            if _tc_rows_ok(n):
+                _tc_bwd_data_acc(dz0, 128, w0g, D1[:, 64:], 128, n)                  # dGeo += dZ0 W0g
+            else:
+                _lib.call("emer_linear_bwd_data", _ptr(dz0), 128, None, 0, ACT_NONE, _ptr(w0g), _ptr(D1[:, 64:]), 128, n,
+                          64, 64, 1, _stream())
+            pad = n_rays * samples - n
+            if pad:                                    # ragged last ray: sum what is there
+                d_rb = torch.zeros((n_rays, 128), **f32)
+                d_rb[:, :64].index_add_(0, torch.arange(n, device=dev) // samples, dz0)
+                d_rb[:, 64:].index_add_(0, torch.arange(n, device=dev) // samples, dz1)
+            else:
+                d_rb = torch.cat([D1.view(n_rays, samples, 128)[:, :, :64].sum(1), dz1.view(n_rays, samples, 64).sum(1)],
+                                 dim=1)
+            dw0 = torch.zeros_like(w0)
+            dw0[:, n_ray_cols:] = dw0g
+            dw1 = torch.zeros_like(w1)
+            dw1[:, :64] = dw1hg[:, :64]
+            dw1[:, 64 + n_ray_cols:] = dw1hg[:, 64:]
+        else:
+            D1[:, 64:].zero_()
+        dgeo = D1[:, 64:]
+        if d_geo is not None:
+            dgeo += d_geo.reshape(n, 64)
+        if d_sigma is not None:
+            # trunc_exp backward (nerf_utils.py:72-75): g * exp(clamp(x, max=15)), x = feats[:, 0] - 1 = log(sigma)
+            dgeo[:, 0] += _f32c(d_sigma).reshape(n) * torch.clamp(sigma, max=3269017.3724721107)
+        if n_feat == 128:
+            dfe = torch.cat([dgeo, torch.zeros((n, 64), **f32) if d_sem is None else _f32c(d_sem.reshape(n, 64))], dim=1)
+            ldf = 128
+        else:
+            dfe, ldf = dgeo, 128
+        dwb1, dbb1 = _layer_bwd_weight(hb, 64, dfe, ldf, wb1, True, n)
+        dzb = torch.empty((n, 64), **f32)
+        _layer_bwd_data(dfe, ldf, wb1, dzb, 64, n, hb, 64, 64)
+        dwb0, dbb0 = _layer_bwd_weight(enc2, ld_enc, dzb, 64, wb0, True, n)
+        d_enc = None
+        if ctx.needs_input_grad[0]:
+            d_enc = torch.empty((n, _pad4(k_enc)), **f32)
+            _layer_bwd_data(dzb, 64, wb0, d_enc, d_enc.shape[1], n, None, 0, 0)
+            d_enc = d_enc[:, :k_enc].reshape(enc_shape)
+        return d_enc, d_rb, None, None, dwb0, dbb0, dwb1, dbb1, dw0, dw1, dw2, db2
+
+
+def field_chain_usable(k_enc: int, n_feat: int, width: int, head: Sequence[Tuple[int, int]]) -> bool:
+    """Whether ``emer_field_fwd`` is specialised for this model: 64-wide base / head layers, a 64-d geometry feature
+    (+ optional 64-d semantic half), a 3-layer colour head with the skip in front of layer 1."""
+    if FIELD_CHAIN != "fused" or LINEAR_IMPL != "tc":
+        return False
+    if k_enc not in CHAIN_K_ENC or n_feat not in (64, 128) or width != 64 or len(head) != 3:
+        return False
+    (o0, i0), (o1, i1), (o2, i2) = head
+    return o0 == 64 and o1 == 64 and o2 == 3 and i2 == 64 and i0 >= 64 and i1 == 64 + i0
+
+
+def field_chain(enc: Tensor, ray_bias: Tensor, samples: int, base, head, want_geo: bool = False):
+    """``base`` = (wb0, bb0, wb1, bb1), ``head`` = (w0, w1, w2, b2) with the reference's column order
+    ([dir | emb | geo] for layer 0, [hidden | dir | emb | geo] for layer 1, radiance_field.py:647, mlp.py:42-43);
+    ``ray_bias`` [R, 128] = [b0 + w0[:, :c] v | b1 + w1[:, 64:64+c] v] for the per-ray input columns v."""
+    return _FieldChain.apply(enc, ray_bias, samples, want_geo, *base, *head)
 
 
 # ----------------------------------------------------------------------------- sampling

@@ -1,0 +1,443 @@
+// The fused field chain on tcgen05: hash-grid features -> base MLP -> density + colour head, ONE persistent kernel,
+// activations never leave the SM.
+//
+// Replaces, for one [N, k_enc] block of hash-grid features (reference: radiance_fields/radiance_field.py)
+//     feats = base_mlp(enc)                       Linear(k_enc,64)-ReLU-Linear(64, 64 [+64 semantic])     :74-80,314-318
+//     sigma = trunc_exp(feats[:, 0] - 1)                                                                  :422
+//     rgb   = sigmoid(rgb_head([dir enc | embedding | geo]))   MLP 113->64, [64|113]->64, 64->3, skip 1  :131-143,622-658
+// which the per-layer path runs as 6 launches with every [N, 64..180] activation round-tripping HBM.
+//
+// Per-ray columns.  The colour head's input is [dir encoding (33) | appearance embedding (16) | geo (64)]; the first 49
+// columns are the same for all samples of a ray, so  W[:, ray cols] * v_ray  is a per-RAY bias, computed once per ray
+// by the caller (ray_bias[R, 128] = [b0 + W0[:, :49] v | b1 + W1[:, 64:113] v]).  The wide layers become
+//     h0 = relu(geo W0g^T + ray_bias0[ray])            64 -> 64
+//     h1 = relu(h0 W1h^T + geo W1g^T + ray_bias1[ray]) 128 -> 64
+// and the [N, 113] / [N, 177] concatenations of the reference never exist.
+//
+// Tensor-core mapping (3xTF32, fp32-accurate, see linear_tc.cu): a tile is 128 points = the 128 TMEM lanes.  Weights
+// (B operands) are resident in shared memory as tf32 hi / lo panels.  ACTIVATIONS LIVE IN TENSOR MEMORY: the epilogue of
+// layer i reads its accumulator with tcgen05.ld, applies bias / ReLU, splits into tf32 hi + lo and writes them back with
+// tcgen05.st as the A operand of layer i+1 (tcgen05.mma with A in TMEM), so no activation ever touches shared memory.
+// Two warpgroups own two tiles in flight (256 TMEM columns each: 128 operand + 128 accumulator); one warp issues the
+// MMAs for both, alternating, so one tile's MMAs run under the other tile's epilogue.
+//
+//   stage  A (TMEM)        B (smem)          D (TMEM)                epilogue
+//   0      enc hi/lo       Wb0 [64 x k_enc]  [0,64)                  +bb0, relu            -> Hb
+//   1      Hb              Wb1 [nf x 64]     [0,nf)                  +bb1; sigma; geo      -> G   (sem -> HBM)
+//   2      G               [W0g;W1g] N=128   [0,64) pre-h0 | [64,128) partial h1   +ray_bias0, relu -> H0
+//   3      H0              W1h               [64,128) accumulate     +ray_bias1, relu      -> H1
+//   4      H1              W2 (3 -> N=16)    [0,16)                  +b2, sigmoid          -> rgb
+//
+// Roofline: per point 3 x (k_enc*64 + 64*nf + 64*128 + 64*64 + 64*16) MACs = 3 x 18 944 (nf = 64) on the tensor pipe
+// (2048 tf32 MAC / clk / SM -> 27.8 clk per point-layer-chain, 0.05 ms for 524 288 points) against
+// (k_enc + 4) * 4 B = 176 B per point of HBM traffic without the training saves (0.014 ms) or + 1 KB with them.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace emer {
+namespace ff {
+
+using namespace emer::tc;
+
+constexpr int ROWS = 128;
+constexpr int EPI_THREADS = 256;              // two warpgroups of 4 warps: warp w owns TMEM lanes 32 (w % 4) ..
+constexpr int THREADS = EPI_THREADS + 32;     // + the MMA-issuing warp
+constexpr int H = 64;                         // hidden / geometry / head width this kernel is specialised for
+
+struct FwdParams {
+    const float* enc; int64_t ld_enc; int k_enc;                  // [N, k_enc], k_enc % 8 == 0, <= 64
+    const float *wb0, *bb0, *wb1, *bb1; int n_feat;               // base MLP; n_feat = 64 (geo) or 128 (geo | semantic)
+    const float* w0g; int64_t ld_w0;                              // colour head layer 0, geo columns   [64, 64]
+    const float *w1h, *w1g; int64_t ld_w1;                        // layer 1: hidden columns, geo columns [64, 64] each
+    const float *w2, *b2;                                         // [3, 64], [3]
+    const float* ray_bias; int samples;                           // [R, 128]; ray of point i = i / samples
+    float *sigma, *rgb;                                           // [N], [N, 3]
+    float *save_hb, *save_hg, *save_h1, *save_sem;                // training saves: [N,64], [N,128]=[h0|geo], [N,64], [N,64]
+    int64_t n;
+};
+
+// shared-memory map (bytes): B operands as K-major SWIZZLE_NONE panels, offset(row, k) = (k/4)*rows*16 + row*16 + (k%4)*4
+struct Smem {
+    int wb0_hi, wb0_lo, wb1_hi, wb1_lo, wg_hi, wg_lo, w1h_hi, w1h_lo, w2_hi, w2_lo, bias, bars, total;
+};
+__host__ __device__ inline Smem smem_map(int k_enc, int n_feat) {
+    Smem m;
+    int o = 0;
+    const int wb0 = (k_enc / 4) * H * 16, wb1 = (H / 4) * n_feat * 16, wg = (H / 4) * 128 * 16, w1h = (H / 4) * H * 16,
+              w2 = (H / 4) * 16 * 16;
+    m.wb0_hi = o; o += wb0; m.wb0_lo = o; o += wb0;
+    m.wb1_hi = o; o += wb1; m.wb1_lo = o; o += wb1;
+    m.wg_hi = o; o += wg; m.wg_lo = o; o += wg;
+    m.w1h_hi = o; o += w1h; m.w1h_lo = o; o += w1h;
+    m.w2_hi = o; o += w2; m.w2_lo = o; o += w2;
+    m.bias = o; o += (64 + 128 + 4) * 4;          // bb0 | bb1 | b2
+    m.bars = o; o += 8 * 8;
+    m.total = o;
+    return m;
+}
+
+// stage one weight matrix w[rows_valid, k_valid] (row stride ld) into hi / lo panels of `rows` x `kpad`
+__device__ __forceinline__ void stage_weight(uint8_t* hi, uint8_t* lo, const float* __restrict__ w, int64_t ld, int rows,
+                                             int rows_valid, int kpad, int k_valid, int row0, int tid, int nthreads) {
+    const int panel = rows * 16;
+    for (int e = tid; e < rows_valid * kpad; e += nthreads) {
+        const int r = e / kpad, k = e - r * kpad;
+        float v = 0.0f;
+        if (k < k_valid) v = __ldg(w + (int64_t)r * ld + k);
+        float h, l;
+        split(v, h, l);
+        const int off = (k >> 2) * panel + (row0 + r) * 16 + (k & 3) * 4;
+        *reinterpret_cast<float*>(hi + off) = h;
+        *reinterpret_cast<float*>(lo + off) = l;
+    }
+}
+
+__device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float h, l;
+        split(v[j], h, l);
+        hi[j] = __float_as_uint(h);
+        lo[j] = __float_as_uint(l);
+    }
+}
+
+__device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+template <int K_ENC>
+__global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const Smem m = smem_map(K_ENC, p.n_feat);
+    float* bias_s = reinterpret_cast<float*>(smem + m.bias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + m.bars);
+    uint64_t* a_full = bars;              // [2] epilogue warpgroup -> issuer: operand of the next layer is in TMEM
+    uint64_t* d_full = bars + 2;          // [2] issuer (tcgen05.commit) -> epilogue warpgroup: accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const bool is_issuer = warp == EPI_THREADS / 32;
+
+    if (tid == 0) {
+        mbar_init(&a_full[0], ROWS);
+        mbar_init(&a_full[1], ROWS);
+        mbar_init(&d_full[0], 1);
+        mbar_init(&d_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512u);
+    }
+    // ---- resident weights (all threads): zero the padded rows first (W2: rows 3..15), then split and scatter
+    for (int i = tid * 16; i < m.bias; i += THREADS * 16) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    stage_weight(smem + m.wb0_hi, smem + m.wb0_lo, p.wb0, K_ENC, H, H, K_ENC, K_ENC, 0, tid, THREADS);
+    stage_weight(smem + m.wb1_hi, smem + m.wb1_lo, p.wb1, H, p.n_feat, p.n_feat, H, H, 0, tid, THREADS);
+    stage_weight(smem + m.wg_hi, smem + m.wg_lo, p.w0g, p.ld_w0, 128, H, H, H, 0, tid, THREADS);
+    stage_weight(smem + m.wg_hi, smem + m.wg_lo, p.w1g, p.ld_w1, 128, H, H, H, H, tid, THREADS);
+    stage_weight(smem + m.w1h_hi, smem + m.w1h_lo, p.w1h, p.ld_w1, H, H, H, H, 0, tid, THREADS);
+    stage_weight(smem + m.w2_hi, smem + m.w2_lo, p.w2, H, 16, 3, H, H, 0, tid, THREADS);
+    for (int e = tid; e < 64 + 128 + 4; e += THREADS) {
+        float v = 0.0f;
+        if (e < 64) v = __ldg(p.bb0 + e);
+        else if (e < 64 + 128) { if (e - 64 < p.n_feat) v = __ldg(p.bb1 + e - 64); }
+        else if (e - 192 < 3) v = __ldg(p.b2 + e - 192);
+        bias_s[e] = v;
+    }
+    fence_async_proxy();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
+    const int64_t pair_stride = (int64_t)gridDim.x * 2;
+    const int iters = (int)((n_tiles + pair_stride - 1) / pair_stride);
+    constexpr int ksteps0 = K_ENC / 8;
+
+    if (is_issuer) {
+        // ================= MMA issuer: stage s of warpgroup 0, stage s of warpgroup 1, stage s+1 of warpgroup 0, ...
+        const uint32_t sbase = smem_u32(smem);
+        const uint64_t d64 = make_desc(0, H * 16, 128), dnf = make_desc(0, p.n_feat * 16, 128),
+                       d128 = make_desc(0, 128 * 16, 128), d16 = make_desc(0, 16 * 16, 128);
+        const uint32_t id64 = make_idesc(128, 64), idnf = make_idesc(128, p.n_feat), id128 = make_idesc(128, 128),
+                       id16 = make_idesc(128, 16);
+        uint32_t ph[2] = {0, 0};
+        for (int it = 0; it < iters; ++it) {
+            for (int stage = 0; stage < 5; ++stage) {
+                for (int wg = 0; wg < 2; ++wg) {
+                    const int64_t tile = ((int64_t)it * gridDim.x + blockIdx.x) * 2 + wg;
+                    if (tile >= n_tiles) continue;
+                    mbar_wait(&a_full[wg], ph[wg]);
+                    ph[wg] ^= 1u;
+                    tc_fence_after();
+                    if (mma_issue_lane(tid)) {
+                        const uint32_t a_hi = tmem_base + (uint32_t)(wg * 256);
+                        const uint32_t a_lo = a_hi + 64u;
+                        uint32_t d = a_hi + 128u;
+                        uint64_t desc;
+                        uint32_t idesc, b_hi, b_lo, panel, acc0 = 0u;
+                        int ksteps = H / 8;
+                        if (stage == 0) { desc = d64; idesc = id64; b_hi = m.wb0_hi; b_lo = m.wb0_lo; panel = H * 16; ksteps = ksteps0; }
+                        else if (stage == 1) { desc = dnf; idesc = idnf; b_hi = m.wb1_hi; b_lo = m.wb1_lo; panel = p.n_feat * 16; }
+                        else if (stage == 2) { desc = d128; idesc = id128; b_hi = m.wg_hi; b_lo = m.wg_lo; panel = 128 * 16; }
+                        else if (stage == 3) { desc = d64; idesc = id64; b_hi = m.w1h_hi; b_lo = m.w1h_lo; panel = H * 16; d += 64u; acc0 = 1u; }
+                        else { desc = d16; idesc = id16; b_hi = m.w2_hi; b_lo = m.w2_lo; panel = 16 * 16; }
+                        const uint32_t bh = (sbase + b_hi) >> 4, bl = (sbase + b_lo) >> 4;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t bo = (uint32_t)(ks * 2 * panel) >> 4;
+                            const uint64_t db_hi = desc | (uint64_t)(bh + bo), db_lo = desc | (uint64_t)(bl + bo);
+                            const uint32_t ah = a_hi + (uint32_t)(ks * 8), al = a_lo + (uint32_t)(ks * 8);
+                            mma_tf32_ts(d, ah, db_hi, idesc, (ks > 0) ? 1u : acc0);
+                            mma_tf32_ts(d, al, db_hi, idesc, 1u);
+                            mma_tf32_ts(d, ah, db_lo, idesc, 1u);
+                        }
+                        tc_commit(&d_full[wg]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warpgroups: one point per thread, the point's row is this thread's TMEM lane
+        const int wg = tid >> 7;
+        const int r_in = tid & 127;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(wg * 256);
+        const uint32_t a_lo = a_hi + 64u;
+        const uint32_t d_addr = a_hi + 128u;
+        const float* bb0_s = bias_s;
+        const float* bb1_s = bias_s + 64;
+        const float* b2_s = bias_s + 192;
+        uint32_t ph = 0;
+        constexpr int NQ = K_ENC / 4;
+
+        float4 x_next[NQ];                       // this thread's enc row of the NEXT tile (prefetched)
+        auto load_enc = [&](int64_t tile) {
+            const int64_t row = tile * ROWS + r_in;
+            const bool ok = tile < n_tiles && row < p.n;
+            const float4* src = reinterpret_cast<const float4*>(p.enc + (ok ? row : 0) * p.ld_enc);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x_next[q] = ok ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        load_enc((int64_t)blockIdx.x * 2 + wg);
+
+        for (int it = 0; it < iters; ++it) {
+            const int64_t tile = ((int64_t)it * gridDim.x + blockIdx.x) * 2 + wg;
+            if (tile >= n_tiles) break;
+            const int64_t row = tile * ROWS + r_in;
+            const bool row_ok = row < p.n;
+            const int64_t ray = (row_ok ? row : (p.n - 1)) / p.samples;
+
+            // ---- stage 0 operand: enc row -> tf32 hi / lo in TMEM
+#pragma unroll
+            for (int c = 0; c < K_ENC / 8; ++c) {
+                {
+                    const float4 u0 = x_next[2 * c], u1 = x_next[2 * c + 1];
+                    const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float h, l;
+                        split(v[j], h, l);
+                        hi[j] = __float_as_uint(h);
+                        lo[j] = __float_as_uint(l);
+                    }
+                    tmem_st8(a_hi + (uint32_t)(c * 8), hi);
+                    tmem_st8(a_lo + (uint32_t)(c * 8), lo);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+            load_enc(tile + pair_stride);        // next tile's row: in flight under this tile's five layers
+
+            // ---- stage 1: Hb = relu(D + bb0)
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + (uint32_t)(c * 16), r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bb0_s[c * 16 + j], 0.0f);
+                if (p.save_hb && row_ok) store16(p.save_hb + row * H + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 2: feats = D + bb1; sigma = exp(feats[0] - 1); geo -> operand; semantic half -> HBM
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + (uint32_t)(c * 16), r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bb1_s[c * 16 + j];
+                if (c == 0 && row_ok) p.sigma[row] = expf(v[0] - 1.0f);
+                if (p.save_hg && row_ok) store16(p.save_hg + row * 128 + H + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+            }
+            if (p.n_feat > H) {
+#pragma unroll
+                for (int c = 4; c < 8; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(d_addr + (uint32_t)(c * 16), r);
+                    tmem_ld_wait();
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bb1_s[c * 16 + j];
+                    if (p.save_sem && row_ok) store16(p.save_sem + row * H + (c - 4) * 16, v);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 3: H0 = relu(D[0,64) + ray_bias0)
+            const float* rb = p.ray_bias + ray * 128;
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + (uint32_t)(c * 16), r);
+                float b[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(rb + c * 16 + j));
+                    b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+                }
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + b[j], 0.0f);
+                if (p.save_hg && row_ok) store16(p.save_hg + row * 128 + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 4: H1 = relu(D[64,128) + ray_bias1)
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + 64u + (uint32_t)(c * 16), r);
+                float b[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(rb + 64 + c * 16 + j));
+                    b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+                }
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + b[j], 0.0f);
+                if (p.save_h1 && row_ok) store16(p.save_h1 + row * H + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 5: rgb = sigmoid(D[0,3) + b2)
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+            {
+                uint32_t r[4];
+                tmem_ld4(d_addr, r);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        p.rgb[row * 3 + j] = 1.0f / (1.0f + expf(-(__uint_as_float(r[j]) + b2_s[j])));
+                }
+            }
+            tc_fence_before();               // the next tile's operand stores follow these loads in program order
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
+}  // namespace ff
+}  // namespace emer
+
+using namespace emer;
+
+extern "C" int emer_field_fwd(const float* enc, int64_t ld_enc, int k_enc, const float* wb0, const float* bb0,
+                              const float* wb1, const float* bb1, int n_feat, const float* w0g, int64_t ld_w0,
+                              const float* w1h, const float* w1g, int64_t ld_w1, const float* w2, const float* b2,
+                              const float* ray_bias, int samples, float* sigma, float* rgb, float* save_hb, float* save_hg,
+                              float* save_h1, float* save_sem, int64_t n, void* stream) {
+    using namespace emer::ff;
+    if (n == 0) return 0;
+    EMER_REQUIRE(enc && wb0 && bb0 && wb1 && bb1 && w0g && w1h && w1g && w2 && b2 && ray_bias && sigma && rgb,
+                 "emer_field_fwd: NULL pointer");
+    EMER_REQUIRE(k_enc == 32 || k_enc == 40 || k_enc == 64, "emer_field_fwd: k_enc=%d (L*F of the grid) must be 32, 40 or 64", k_enc);
+    EMER_REQUIRE(n_feat == 64 || n_feat == 128, "emer_field_fwd: n_feat=%d must be 64 or 128", n_feat);
+    EMER_REQUIRE(samples > 0, "emer_field_fwd: samples per ray must be positive");
+    EMER_REQUIRE(ld_enc % 4 == 0 && ((uintptr_t)enc & 15) == 0, "emer_field_fwd: enc rows must be 16-byte aligned");
+    EMER_REQUIRE(((uintptr_t)ray_bias & 15) == 0, "emer_field_fwd: ray_bias must be 16-byte aligned");
+    EMER_REQUIRE((((uintptr_t)save_hb | (uintptr_t)save_hg | (uintptr_t)save_h1 | (uintptr_t)save_sem) & 15) == 0,
+                 "emer_field_fwd: save buffers must be 16-byte aligned");
+    EMER_REQUIRE(n_feat == 64 || save_sem, "emer_field_fwd: the semantic half needs its output buffer");
+    FwdParams p{};
+    p.enc = enc; p.ld_enc = ld_enc; p.k_enc = k_enc; p.wb0 = wb0; p.bb0 = bb0; p.wb1 = wb1; p.bb1 = bb1; p.n_feat = n_feat;
+    p.w0g = w0g; p.ld_w0 = ld_w0; p.w1h = w1h; p.w1g = w1g; p.ld_w1 = ld_w1; p.w2 = w2; p.b2 = b2;
+    p.ray_bias = ray_bias; p.samples = samples; p.sigma = sigma; p.rgb = rgb;
+    p.save_hb = save_hb; p.save_hg = save_hg; p.save_h1 = save_h1; p.save_sem = save_sem; p.n = n;
+    const Smem m = smem_map(k_enc, n_feat);
+    const size_t smem = (size_t)m.total;
+    EMER_REQUIRE(smem <= 227 * 1024, "emer_field_fwd: %zu B of shared memory needed", smem);
+    const int64_t n_tiles = ceil_div(n, ROWS);
+    int64_t grid = sm_count();
+    if (grid > ceil_div(n_tiles, 2)) grid = ceil_div(n_tiles, 2);
+    auto launch = [&](auto kernel, size_t& configured) -> int {
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                set_error("emer_field_fwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+                return -2;
+            }
+            configured = smem;
+        }
+        kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+        return 0;
+    };
+    static size_t configured_dev[3][64] = {{0}};          // the attribute is per kernel and per device
+    const int dev = current_device();
+    int rc;
+    if (k_enc == 32) rc = launch(field_fwd_kernel<32>, configured_dev[0][dev]);
+    else if (k_enc == 40) rc = launch(field_fwd_kernel<40>, configured_dev[1][dev]);
+    else rc = launch(field_fwd_kernel<64>, configured_dev[2][dev]);
+    if (rc) return rc;
+    return check_launch("emer_field_fwd");
+}

@@ -237,6 +237,44 @@ class RadianceField(nn.Module):
         return _ops.mlp_chain(rgb_in, [l0.weight[:, self._perm0], l1.weight[:, self._perm1], l2.weight],
                               [l0.bias, l1.bias, l2.bias], _ops.ACT_SIGMOID, 1, catbuf=catbuf)
 
+    # ------------------------------------------------------------------ fused chain
+    def _chain_usable(self, encoder: HashEncoder, base: nn.Sequential) -> bool:
+        lin = [m for m in base if isinstance(m, nn.Linear)]
+        if len(lin) != 2 or len(self.rgb_head.layers) != 3 or self.rgb_head.skip_connections != [1]:
+            return False
+        head = [(l.out_features, l.in_features) for l in self.rgb_head.layers]
+        return (self.geometry_feature_dim == 64 and lin[0].in_features == encoder.n_output_dims
+                and lin[1].in_features == lin[0].out_features
+                and _ops.field_chain_usable(encoder.n_output_dims, lin[1].out_features, lin[0].out_features, head))
+
+    def _ray_bias(self, tail) -> Tensor:
+        """[R, 128]: what the per-ray input columns of the colour head -- direction encoding and appearance embedding,
+        the same for every sample of a ray -- contribute to its first two layers, biases included:
+        [b0 + W0[:, :c] v | b1 + W1[:, 64:64+c] v] with v = [sinenc((d+1)/2) | emb[idx]] (radiance_field.py:629-647;
+        W1's input is [hidden | v | geo], mlp.py:42-43).  8192 rows instead of 524 288."""
+        dirs, idx, emb = tail
+        v = self.direction_encoding((dirs + 1.0) / 2.0)
+        if emb is not None:
+            v = torch.cat([v, emb[idx]], dim=-1)
+        c = v.shape[-1]
+        l0, l1, _ = self.rgb_head.layers
+        h = l0.out_features
+        w = torch.cat([l0.weight[:, :c], l1.weight[:, h:h + c]], dim=0)
+        return _ops.linear(_ops.cat_pad4([v]), w, torch.cat([l0.bias, l1.bias]))
+
+    def _run_chain(self, encoder: HashEncoder, base: nn.Sequential, coords: Tensor, ray_bias: Tensor,
+                   want_geo: bool = False):
+        """(density [R,S], rgb [R,S,3], geo [R,S,64] | None, sem [R,S,64] | None) for grid coordinates [R,S,D]."""
+        r, s_ = coords.shape[:2]
+        enc = encoder(coords.reshape(-1, coords.shape[-1]))
+        lin = [m for m in base if isinstance(m, nn.Linear)]
+        l0, l1, l2 = self.rgb_head.layers
+        sigma, rgb, geo, sem = _ops.field_chain(
+            enc, ray_bias, s_, (lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias),
+            (l0.weight, l1.weight, l2.weight, l2.bias), want_geo=want_geo)
+        return (sigma.view(r, s_), rgb.view(r, s_, 3), None if geo is None else geo.view(r, s_, -1),
+                None if sem is None else sem.view(r, s_, -1))
+
     # ------------------------------------------------------------------ building blocks
     def contract_points(self, positions: Tensor) -> Tensor:
         return _contract_points(positions, self.aabb, self.unbounded)
@@ -293,39 +331,55 @@ class RadianceField(nn.Module):
     ) -> Dict[str, Tensor]:
         out: Dict[str, Tensor] = {}
         G, S = self.geometry_feature_dim, self.semantic_feature_dim
-        feats, normed = self.forward_static_hash(positions)
-        geo, sem = feats[..., :G], feats[..., G:G + S]
-        tail = None if (return_density_only or feats.dim() != 3) else self._tail_inputs(directions, data_dict)
-        if tail is not None:
-            static_density, rgb_in_static = self._field_tail(feats, tail)
+        tail = None if (return_density_only or positions.dim() != 3) else self._tail_inputs(directions, data_dict)
+        # the fused chain (base MLP + density + colour head in one tcgen05 kernel) when the model has its shape
+        chain = tail is not None and self._chain_usable(self.xyz_encoder, self.base_mlp)
+        rgb_in_static = static_rgb = None
+        if chain:
+            ray_bias = self._ray_bias(tail)
+            normed = self.contract_points(positions)
+            static_density, static_rgb, _, sem = self._run_chain(self.xyz_encoder, self.base_mlp, normed, ray_bias)
         else:
-            static_density = self._density(feats)
+            feats, normed = self.forward_static_hash(positions)
+            geo, sem = feats[..., :G], feats[..., G:G + S]
+            if tail is not None:
+                static_density, rgb_in_static = self._field_tail(feats, tail)
+            else:
+                static_density = self._density(feats)
 
         dynamic_on = self.dynamic_xyz_encoder is not None and self._has_time(data_dict)
         if dynamic_on:
             t = data_dict["normed_timestamps"] if "normed_timestamps" in data_dict \
                 else data_dict["lidar_normed_timestamps"]
-            dyn_feats, dyn_enc = self.forward_dynamic_hash(normed, t, return_hash_encodings=True)
-            if self.flow_xyz_encoder is not None:
-                flow = self.forward_flow_hash(normed, t)
-                fwd, bwd = flow[..., :3], flow[..., 3:]
-                out["forward_flow"], out["backward_flow"] = fwd, bwd
-                agg = self.temporal_aggregation(positions, t, fwd, bwd, dyn_feats)
-                dyn_feats = agg["dynamic_feats"]
-                agg["current_dynamic_hash_encodings"] = dyn_enc
-                out.update(agg)
-            dyn_geo, dyn_sem = dyn_feats[..., :G], dyn_feats[..., G:G + S]
-            if tail is not None:
-                dynamic_density, rgb_in_dynamic = self._field_tail(dyn_feats, tail)
+            dynamic_rgb = None
+            if chain and self.flow_xyz_encoder is None and self._chain_usable(self.dynamic_xyz_encoder,
+                                                                              self.dynamic_base_mlp):
+                # no temporal aggregation between the base MLP and the head: the dynamic branch is one chain too
+                dynamic_density, dynamic_rgb, dyn_geo, dyn_sem = self._run_chain(
+                    self.dynamic_xyz_encoder, self.dynamic_base_mlp, self._space_time(normed, t), ray_bias,
+                    want_geo=self.enable_shadow_head)
             else:
-                dynamic_density = self._density(dyn_feats)
+                dyn_feats, dyn_enc = self.forward_dynamic_hash(normed, t, return_hash_encodings=True)
+                if self.flow_xyz_encoder is not None:
+                    flow = self.forward_flow_hash(normed, t)
+                    fwd, bwd = flow[..., :3], flow[..., 3:]
+                    out["forward_flow"], out["backward_flow"] = fwd, bwd
+                    agg = self.temporal_aggregation(positions, t, fwd, bwd, dyn_feats)
+                    dyn_feats = agg["dynamic_feats"]
+                    agg["current_dynamic_hash_encodings"] = dyn_enc
+                    out.update(agg)
+                dyn_geo, dyn_sem = dyn_feats[..., :G], dyn_feats[..., G:G + S]
+                if tail is not None:
+                    dynamic_density, rgb_in_dynamic = self._field_tail(dyn_feats, tail)
+                else:
+                    dynamic_density = self._density(dyn_feats)
             density = static_density + dynamic_density
             out.update(density=density, static_density=static_density, dynamic_density=dynamic_density)
             if return_density_only:
                 return out
             if tail is not None:
-                out["dynamic_rgb"] = self._rgb_from_tail(rgb_in_dynamic)
-                out["static_rgb"] = self._rgb_from_tail(rgb_in_static)
+                out["dynamic_rgb"] = dynamic_rgb if dynamic_rgb is not None else self._rgb_from_tail(rgb_in_dynamic)
+                out["static_rgb"] = static_rgb if static_rgb is not None else self._rgb_from_tail(rgb_in_static)
             elif directions is not None:
                 colours = self.query_rgb(directions, geo, dyn_geo, data_dict=data_dict)
                 out["dynamic_rgb"] = colours["dynamic_rgb"]
@@ -348,7 +402,7 @@ class RadianceField(nn.Module):
                 # a dynamic field asked for colour without timestamps fails like the reference's query_rgb
                 # (radiance_field.py:651-654)
                 assert self.dynamic_xyz_encoder is None, "Dynamic geometry features are not provided."
-                out["rgb"] = self._rgb_from_tail(rgb_in_static)
+                out["rgb"] = static_rgb if static_rgb is not None else self._rgb_from_tail(rgb_in_static)
             elif directions is not None:
                 out["rgb"] = self.query_rgb(directions, geo, data_dict=data_dict)["rgb"]
 

@@ -157,6 +157,27 @@ int emer_field_tail_bwd(const float* feats, int64_t ld_feats, float* d_out, int6
                         const float* d_sigma, const int64_t* idx, float* d_emb, int e_dim, int64_t n_rays,
                         int n_samples, void* stream);
 
+/* ---- the fused field chain (csrc/field_fused.cu): base MLP -> density + colour head in ONE tcgen05 kernel with the
+ *      activations in tensor memory.  Replaces the chain of nn.Linear / torch.cat / trunc_exp / sigmoid calls of
+ *      radiance_fields/radiance_field.py:74-80,314-318 (base_mlp), :422 (density), :131-143,622-658 (query_rgb) and
+ *      radiance_fields/mlp.py:38-46 for one block of hash-grid features.
+ *   enc[N, k_enc] (k_enc = 32, 40 or 64; rows 16-byte aligned)
+ *   feats = relu(enc wb0^T + bb0) wb1^T + bb1        wb0 [64, k_enc], wb1 [n_feat, 64], n_feat = 64 | 128
+ *   sigma[n] = exp(feats[n, 0] - 1)
+ *   h0 = relu(geo w0g^T + ray_bias[ray, 0:64]),  h1 = relu(h0 w1h^T + geo w1g^T + ray_bias[ray, 64:128]),
+ *   rgb[n, 0:3] = sigmoid(h1 w2^T + b2)              geo = feats[:, 0:64], ray = n / samples
+ *   w0g / w1h / w1g are [64, 64] column blocks of the colour head's [64, 113] / [64, 177] weights (row strides ld_w0 /
+ *   ld_w1); the per-ray input columns (direction encoding, appearance embedding) and the two layer biases arrive folded
+ *   into ray_bias[R, 128] by the caller.
+ *   save_hb [N,64] = relu(.) of the base layer, save_hg [N,128] = [h0 | geo], save_h1 [N,64], save_sem [N,64] =
+ *   feats[:, 64:128]: what the backward pass needs; each may be NULL (inference), save_sem is required when
+ *   n_feat == 128. */
+int emer_field_fwd(const float* enc, int64_t ld_enc, int k_enc, const float* wb0, const float* bb0,
+                   const float* wb1, const float* bb1, int n_feat, const float* w0g, int64_t ld_w0,
+                   const float* w1h, const float* w1g, int64_t ld_w1, const float* w2, const float* b2,
+                   const float* ray_bias, int samples, float* sigma, float* rgb, float* save_hb, float* save_hg,
+                   float* save_h1, float* save_sem, int64_t n, void* stream);
+
 /* ---- volume rendering along rays (replaces nerfacc.render_transmittance_from_density /
  *      render_weight_from_density / accumulate_along_rays and the torch cumsum/searchsorted of
  *      radiance_fields/render_utils.py:73-115) ---------------------------------------------- */

@@ -572,9 +572,13 @@ def render_rays(
     training: bool, proposal_requires_grad: bool = False, return_decomposition: bool = False,
     prefix: str = "", render_chunk_size: int = 16384,
     jitters: Optional[List[Tensor]] = None, noise: Optional[Tensor] = None,
-    rng_record: Optional[dict] = None,
+    rng_record: Optional[dict] = None, prop_sigma_scale: float = 1.0,
 ):
-    """render_rays, render_utils.py:290-389.  Returns (render_results, prop_cache)."""
+    """render_rays, render_utils.py:290-389.  Returns (render_results, prop_cache).
+
+    ``prop_sigma_scale`` (not in the reference; 1.0 = the reference's arithmetic) multiplies the proposal densities:
+    the parity tests use 1 +- 1e-6 to measure how far a last-bit difference in the proposal CDFs moves each ray's
+    samples (inverse-CDF resampling is ill-conditioned where a CDF is flat), see :func:`sample_stability`."""
     shape = data_dict[prefix + "origins"].shape
     if len(shape) == 3:
         n_rays = shape[0] * shape[1]
@@ -592,7 +596,10 @@ def render_rays(
         def prop_fn(t0, t1, j):
             d = cd[prefix + "viewdirs"][..., None, :]
             pos = o + d * (t0 + t1)[..., None] / 2.0
-            return density_field_forward(prop_sds[j], prop_specs[j], pos)
+            res = density_field_forward(prop_sds[j], prop_specs[j], pos)
+            if prop_sigma_scale != 1.0:
+                res = {"density": res["density"] * prop_sigma_scale}
+            return res
 
         def query_fn(t0, t1):
             S = t0.shape[-1]
@@ -628,3 +635,19 @@ def render_rays(
         merged[k] = v.reshape(list(shape[:-1]) + list(v.shape[1:]))
     merged["extras"] = extras
     return merged, cache
+
+
+def sample_stability(render, base_t_vals: Tensor, eps: Sequence[float] = (2e-6, -2e-6, 1e-6, -1e-6, 3e-7, -3e-7, 1e-7, -1e-7),
+                     threshold: float = 1e-5) -> Tensor:
+    """Which rays have WELL-CONDITIONED samples.  ``render(scale)`` renders with the proposal densities multiplied by
+    ``scale`` (``render_rays(..., prop_sigma_scale=scale)``) and returns its results; a ray is stable when none of the
+    1 + eps probes -- differences of the size of one expf / summation-order ulp in the proposal CDFs, which no two
+    implementations (this oracle, tiny-cuda-nn + nerfacc on a GPU, this repository's kernels) share -- moves any of
+    its final sample midpoints by more than ``threshold`` relative.  Where a proposal CDF is flat (transmittance
+    already ~0, or empty space), the inverse-CDF resampling amplifies such a difference by orders of magnitude, and
+    per-sample quantities and expected depth of that ray are not comparable across implementations.  [R] bool."""
+    worst = torch.zeros(base_t_vals.shape[0])
+    for e in eps:
+        t = render(1.0 + e)["extras"]["t_vals"]
+        worst = torch.maximum(worst, ((t - base_t_vals).abs() / base_t_vals.abs()).amax(dim=-1))
+    return worst <= threshold

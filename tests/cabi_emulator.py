@@ -422,6 +422,38 @@ def emer_accumulate_bwd(w, v, g, dw, dv, n_rays, n_samples, c, stream):
             _view(dv, n_rays * n_samples, c).copy_((ww[..., None] * gg[:, None, :]).reshape(-1, c))
 
 
+# ----------------------------------------------------------------------------- fused field chain
+def emer_field_fwd(enc, ld_enc, k_enc, wb0, bb0, wb1, bb1, n_feat, w0g, ld_w0, w1h, w1g, ld_w1, w2, b2, ray_bias,
+                   samples, sigma, rgb, save_hb, save_hg, save_h1, save_sem, n, stream):
+    _require(k_enc in (32, 40, 64), f"emer_field_fwd: k_enc={k_enc} (L*F of the grid) must be 32, 40 or 64")
+    _require(n_feat in (64, 128), f"emer_field_fwd: n_feat={n_feat} must be 64 or 128")
+    _require(samples > 0, "emer_field_fwd: samples per ray must be positive")
+    _require(ld_enc % 4 == 0 and _aligned16(enc, ray_bias, save_hb, save_hg, save_h1, save_sem),
+             "emer_field_fwd: rows must be 16-byte aligned")
+    _require(n_feat == 64 or _addr(save_sem), "emer_field_fwd: the semantic half needs its output buffer")
+    if n == 0:
+        return
+    n_rays = (n + samples - 1) // samples
+    with torch.no_grad():
+        x = _view(enc, n, k_enc, ld_enc)
+        hb = torch.relu(x @ _view(wb0, 64, k_enc).T + _vec(bb0, 64))
+        feats = hb @ _view(wb1, n_feat, 64).T + _vec(bb1, n_feat)
+        geo = feats[:, :64]
+        rb = _view(ray_bias, n_rays, 128)[torch.arange(n) // samples]
+        h0 = torch.relu(geo @ _view(w0g, 64, 64, ld_w0).T + rb[:, :64])
+        h1 = torch.relu(h0 @ _view(w1h, 64, 64, ld_w1).T + geo @ _view(w1g, 64, 64, ld_w1).T + rb[:, 64:])
+        _vec(sigma, n).copy_(torch.exp(feats[:, 0] - 1.0))
+        _view(rgb, n, 3).copy_(torch.sigmoid(h1 @ _view(w2, 3, 64).T + _vec(b2, 3)))
+        if _addr(save_hb):
+            _view(save_hb, n, 64).copy_(hb)
+        if _addr(save_hg):
+            _view(save_hg, n, 128).copy_(torch.cat([h0, geo], -1))
+        if _addr(save_h1):
+            _view(save_h1, n, 64).copy_(h1)
+        if n_feat == 128:
+            _view(save_sem, n, 64).copy_(feats[:, 64:])
+
+
 # ----------------------------------------------------------------------------- dispatch
 def call(name: str, *args) -> None:
     """Stand-in for ``emernerf_b200._lib.call``: same names, same positional arguments."""

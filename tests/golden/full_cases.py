@@ -123,3 +123,22 @@ def projections(grad: torch.Tensor, n_proj: int = 16, seed: int = 5) -> torch.Te
         out.append((g * sign).sum())
     out += [g.abs().sum(), g.square().sum().sqrt()]
     return torch.stack(out)
+
+
+def mask_rays(out: dict, keep: torch.Tensor) -> dict:
+    """render_rays results restricted to the rays ``keep`` ([R] bool), extras included."""
+    res = {}
+    for k, v in out.items():
+        if isinstance(v, dict):
+            res[k] = mask_rays(v, keep)
+        else:
+            res[k] = v[keep.to(v.device)]
+    return res
+
+
+def mask_prop_cache(cache: list, keep: torch.Tensor) -> None:
+    """Restrict the estimator's cached (intervals, cdfs, level) entries to the rays ``keep``, in place -- the
+    proposal loss is then the reference's own ``compute_loss`` over those rays."""
+    for i, (iv, cdfs, lvl) in enumerate(cache):
+        iv.vals = iv.vals[keep.to(iv.vals.device)]
+        cache[i] = (iv, None if cdfs is None else cdfs[keep.to(cdfs.device)], lvl)

@@ -46,6 +46,22 @@ REF = types.SimpleNamespace(HashEncoder=HashEncoder, RadianceField=RadianceField
 SEED_RENDER = 777
 
 
+def stable_rays(field, props, batch, training, prefix, base_t_vals, jitters=None, noise=None):
+    """hotpath.sample_stability for one pass (same weights, same random draws)."""
+    fsd = adapters.cpu_state_dict(field)
+    psd = [adapters.cpu_state_dict(p) for p in props]
+    fspec, pspec = adapters.spec_from_module(field), [adapters.spec_from_module(p) for p in props]
+
+    def render(scale):
+        with torch.no_grad():
+            return hotpath.render_rays(fsd, fspec, psd, pspec, batch, num_samples=fc.NUM_SAMPLES,
+                                       prop_samples=fc.PROP_SAMPLES, near_plane=fc.NEAR, far_plane=fc.FAR,
+                                       training=training, prefix=prefix, jitters=jitters, noise=noise,
+                                       prop_sigma_scale=scale)[0]
+
+    return hotpath.sample_stability(render, base_t_vals)
+
+
 def oracle_render(field, props, batch, training, prg, decomp, prefix, rec=None):
     fsd = adapters.cpu_state_dict(field, requires_grad=training)
     psd = [adapters.cpu_state_dict(p, requires_grad=training) for p in props]
@@ -80,20 +96,26 @@ def run(variant: str):
     field.train(); [p.train() for p in props]; est.train()
     torch.manual_seed(SEED_RENDER)
     ref = render_rays(field, est, props, batch, cfg, proposal_requires_grad=True)
-    prop_loss = est.compute_loss(ref["extras"]["trans"], 1024.0)
-    pnames = [(i, k) for i, p in enumerate(props) for k, _ in p.named_parameters()]
-    pg = torch.autograd.grad(prop_loss, [q for p in props for q in p.parameters()], allow_unused=True)
-    loss = adapters.parity_loss(ref)
-    names = [k for k, _ in field.named_parameters()]
-    fg = torch.autograd.grad(loss, [v for _, v in field.named_parameters()], allow_unused=True)
-
     rec = {}
     torch.manual_seed(SEED_RENDER)
     orc, cache, fsd, psd = oracle_render(field, props, batch, True, True, False, "", rec)
     check(f"{variant}/train", ref, orc)
-    o_prop_loss = hotpath.proposal_loss(cache, orc["extras"]["trans"], (0.03, 0.003), 1024.0)
+    # the scalar losses (and their gradients) are taken over the rays whose samples are well-conditioned
+    # (hotpath.sample_stability): on the others no two implementations place the samples alike
+    keep = stable_rays(field, props, batch, True, "", ref["extras"]["t_vals"].detach(), rec["jitters"], rec.get("noise"))
+    store["train/stable"] = keep.numpy()
+    fc.mask_prop_cache(est.prop_cache, keep)
+    prop_loss = est.compute_loss(ref["extras"]["trans"][keep], 1024.0)
+    pnames = [(i, k) for i, p in enumerate(props) for k, _ in p.named_parameters()]
+    pg = torch.autograd.grad(prop_loss, [q for p in props for q in p.parameters()], allow_unused=True)
+    loss = adapters.parity_loss(fc.mask_rays(ref, keep))
+    names = [k for k, _ in field.named_parameters()]
+    fg = torch.autograd.grad(loss, [v for _, v in field.named_parameters()], allow_unused=True)
+
+    fc.mask_prop_cache(cache, keep)
+    o_prop_loss = hotpath.proposal_loss(cache, orc["extras"]["trans"][keep], (0.03, 0.003), 1024.0)
     assert abs(o_prop_loss.item() - prop_loss.item()) <= 1e-5 * max(1.0, abs(prop_loss.item()))
-    o_loss = adapters.parity_loss(orc)
+    o_loss = adapters.parity_loss(fc.mask_rays(orc, keep))
     ofg = torch.autograd.grad(o_loss, [fsd[k] for k in names], allow_unused=True)
     for k, a, b in zip(names, fg, ofg):
         if a is None:
@@ -131,6 +153,7 @@ def run(variant: str):
         orc, _, _, _ = oracle_render(field, props, batch, False, False, True, "")
     check(f"{variant}/eval", ref, orc)
     flat("eval/out", ref, store)
+    store["eval/stable"] = stable_rays(field, props, batch, False, "", ref["extras"]["t_vals"]).numpy()
 
     # ---------------- lidar pass (density only), training mode, no proposal grads
     lb = fc.make_batch(variant, seed=7, lidar=True)
@@ -147,6 +170,10 @@ def run(variant: str):
         store[f"lidar/jitter{i}"] = jt.numpy()
     if "noise" in rec:
         store["lidar/noise"] = rec["noise"].detach().numpy()
+    store["lidar/stable"] = stable_rays(field, props, lb, True, "lidar_", ref["extras"]["t_vals"].detach(),
+                                        rec["jitters"], rec.get("noise")).numpy()
+    print(f"  stable rays: train {int(store['train/stable'].sum())} eval {int(store['eval/stable'].sum())} "
+          f"lidar {int(store['lidar/stable'].sum())} of {fc.N_RAYS}")
 
     path = os.path.join(HERE, f"full_{variant}.npz")
     np.savez_compressed(path, **store)

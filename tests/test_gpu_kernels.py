@@ -485,3 +485,72 @@ def test_colour_head_chain_skip_variants(impl, shared, n, monkeypatch):
     assert rel_err(xg.grad, xd.grad) < 2e-5
     for a, b in zip(wg + bg, wd + bd):
         assert rel_err(a.grad, b.grad) < 2e-5
+
+
+# ----------------------------------------------------------------------------- fused field chain (tcgen05, TMEM-resident)
+def _chain_reference(enc, rb, S, wb0, bb0, wb1, bb1, w0, w1, w2, b2, c):
+    d = lambda t: t.double()
+    hb = torch.relu(d(enc) @ d(wb0).T + d(bb0))
+    feats = hb @ d(wb1).T + d(bb1)
+    geo = feats[:, :64]
+    r = d(rb)[torch.arange(enc.shape[0], device=enc.device) // S]
+    h0 = torch.relu(geo @ d(w0)[:, c:].T + r[:, :64])
+    h1 = torch.relu(h0 @ d(w1)[:, :64].T + geo @ d(w1)[:, 64 + c:].T + r[:, 64:])
+    rgb = torch.sigmoid(h1 @ d(w2).T + d(b2))
+    return torch.exp(feats[:, 0] - 1), rgb, geo, feats[:, 64:], hb, h0, h1
+
+
+@pytest.mark.parametrize("k_enc,n_feat,n,S,c", [(40, 64, 128 * 6 + 37, 64, 49), (40, 128, 4096, 48, 49), (32, 64, 333, 16, 33),
+                                                (64, 64, 128 * 300, 64, 49)])
+def test_field_chain_forward_backward_vs_fp64(k_enc, n_feat, n, S, c):
+    """emer_field_fwd (csrc/field_fused.cu): outputs within 2e-5 of an fp64 restatement of the chain (3xTF32 in TMEM),
+    ragged last tile / last ray, both warpgroups and many tiles per CTA; gradients of every input through the op's
+    backward within 2e-4 of fp64 autograd."""
+    from emernerf_b200 import _ops
+
+    gen = torch.Generator().manual_seed(k_enc + n)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=gen) * scale).to(DEV)
+    R = (n + S - 1) // S
+    enc = rnd(n, k_enc, scale=0.5).requires_grad_(True)
+    rb = rnd(R, 128, scale=0.3).requires_grad_(True)
+    ws = [rnd(64, k_enc, scale=0.2), rnd(64, scale=0.1), rnd(n_feat, 64, scale=0.15), rnd(n_feat, scale=0.1),
+          rnd(64, 64 + c, scale=0.12), rnd(64, 128 + c, scale=0.1), rnd(3, 64, scale=0.2), rnd(3, scale=0.1)]
+    ws = [w.requires_grad_(True) for w in ws]
+    sigma, rgb, geo, sem = _ops.field_chain(enc, rb, S, ws[:4], ws[4:], want_geo=True)
+    want = _chain_reference(enc.detach(), rb.detach(), S, *[w.detach() for w in ws], c)
+    assert rel_err(sigma, want[0]) < 2e-5 and rel_err(rgb, want[1]) < 2e-5 and rel_err(geo, want[2]) < 2e-5
+    if n_feat == 128:
+        assert rel_err(sem, want[3]) < 2e-5
+    else:
+        assert sem is None
+    # gradients: a scalar that touches every output
+    g_s, g_c, g_g = rnd(n), rnd(n, 3), rnd(n, 64, scale=0.1)
+    loss = (sigma * g_s).sum() + (rgb * g_c).sum() + (geo * g_g).sum() + (0 if sem is None else (sem * g_g).sum())
+    got = torch.autograd.grad(loss, [enc, rb] + ws)
+    enc64, rb64 = enc.detach().double().requires_grad_(True), rb.detach().double().requires_grad_(True)
+    ws64 = [w.detach().double().requires_grad_(True) for w in ws]
+    r = _chain_reference(enc64, rb64, S, *ws64, c)
+    loss64 = (r[0] * g_s).sum() + (r[1] * g_c).sum() + (r[2] * g_g).sum() + (0 if n_feat == 64 else (r[3] * g_g).sum())
+    want_g = torch.autograd.grad(loss64, [enc64, rb64] + ws64)
+    for name, a, b in zip(["enc", "ray_bias", "wb0", "bb0", "wb1", "bb1", "w0", "w1", "w2", "b2"], got, want_g):
+        assert rel_err(a, b) < 2e-4, (name, rel_err(a, b))
+    # per-ray columns of the head weights belong to the ray-bias product, not to this op
+    assert float(got[6][:, :c].abs().max()) == 0.0 and float(got[7][:, 64:64 + c].abs().max()) == 0.0
+
+
+def test_field_chain_inference_writes_no_saves():
+    """Under no_grad the op allocates neither the hidden activations nor [h0 | geo] (inference traffic only) and gives
+    the same outputs as the training call."""
+    from emernerf_b200 import _ops
+
+    gen = torch.Generator().manual_seed(3)
+    rnd = lambda *s, scale=1.0: (torch.randn(*s, generator=gen) * scale).to(DEV)
+    n, S = 128 * 40, 64
+    enc, rb = rnd(n, 40, scale=0.5), rnd(n // S, 128, scale=0.3)
+    ws = [rnd(64, 40, scale=0.2), rnd(64), rnd(64, 64, scale=0.15), rnd(64), rnd(64, 113, scale=0.12),
+          rnd(64, 177, scale=0.1), rnd(3, 64, scale=0.2), rnd(3)]
+    with torch.no_grad():
+        s0, c0, g0, _ = _ops.field_chain(enc, rb, S, ws[:4], ws[4:])
+    assert g0 is None
+    s1, c1, _, _ = _ops.field_chain(enc.clone().requires_grad_(True), rb, S, ws[:4], ws[4:])
+    assert torch.equal(s0, s1) and torch.equal(c0, c1)
