@@ -41,6 +41,8 @@ _SIGNATURES = {
     "emer_field_tail_bwd": [_P, c_int64, _P, c_int64, c_int, _P, _P, _P, c_int, c_int64, c_int, _P],
     "emer_field_fwd": [_P, c_int64, c_int, _P, _P, _P, _P, c_int, _P, c_int64, _P, _P, c_int64, _P, _P, _P, c_int, _P, _P, _P,
                        _P, _P, _P, c_int64, _P],
+    "emer_field_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P,
+                       _P, _P, c_int64, _P, c_int, c_int64, _P],
     "emer_composite_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P],
     "emer_composite_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P],
     "emer_accumulate_fwd": [_P, _P, _P, c_int64, c_int, c_int, _P],
@@ -113,6 +115,8 @@ def tag_of(name: str, args) -> str:
             return f"k{args[7]}_o{args[8]}_N{args[6]}"
         if name == "emer_linear_bwd_weight":
             return f"k{args[10]}_o{args[11]}_N{args[9]}"
+        if name == "emer_field_bwd":
+            return f"k{args[10]}_f{args[12]}_N{args[27]}"
         if name == "emer_field_fwd":
             return f"k{args[2]}_f{args[7]}_N{args[23]}" + ("_save" if args[19].value else "")
     except Exception:

@@ -544,6 +544,7 @@ def field_tail(feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional
 
 # ----------------------------------------------------------------------------- fused field chain
 FIELD_CHAIN = os.environ.get("EMER_FIELD_CHAIN", "fused")      # "layers": the per-layer path (A/B and debugging switch)
+CHAIN_BWD = os.environ.get("EMER_CHAIN_BWD", "fused")          # "layers": data gradients layer by layer (A/B switch)
 CHAIN_K_ENC = (32, 40, 64)
 
 
@@ -609,61 +610,84 @@ class _FieldChain(torch.autograd.Function):
         if d_sigma is None and d_rgb is None and d_geo is None and d_sem is None:
             return none
         n_rays = (n + samples - 1) // samples
-        # D1 = [dZ0 | dGeo] side by side (row stride 128): the hidden-layer gradient of head layer 0 and the
-        # gradient arriving at the geometry features from both head layers
-        D1 = torch.empty((n, 128), **f32)
-        dw0 = dw1 = dw2 = db2 = d_rb = None
-        if d_rgb is not None:
-            dz2 = _f32c(d_rgb.reshape(n, 3)) * (rgb * (1.0 - rgb))
-            dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n)
+        w1hg = torch.cat([w1[:, :64], w1[:, 64 + n_ray_cols:]], dim=1)            # [64, 128] = [hidden | geo] columns
+        w0g = w0[:, n_ray_cols:].contiguous()
+        D1 = torch.empty((n, 128), **f32)          # [dZ0 | dF] side by side (row stride 128)
+        dw0 = dw1 = dw2 = db2 = d_rb = d_enc = None
+        c = lambda g, w: None if g is None else _f32c(g.reshape(n, w))
+        d_geo, d_sem = c(d_geo, 64), c(d_sem, 64)
+        if CHAIN_BWD == "fused" and samples % 32 == 0 and _tc_rows_ok(n):
+            # ---- the whole data path in one kernel (csrc/field_fused.cu: field_bwd_kernel)
+            d_rgb2 = c(d_rgb, 3)
+            d_sig = None if d_sigma is None else _f32c(d_sigma).reshape(n)
+            dz2 = torch.empty((n, 3), **f32) if d_rgb is not None else None
             dz1 = torch.empty((n, 64), **f32)
-            _layer_bwd_data(dz2, 3, w2, dz1, 64, n, h1, 64, 64)                       # relu'(h1) applied
-            w1hg = torch.cat([w1[:, :64], w1[:, 64 + n_ray_cols:]], dim=1)            # [64, 128] = [hidden | geo] columns
-            dw1hg, _ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)
-            _layer_bwd_data(dz1, 64, w1hg, D1, 128, n, hg, 128, 64)                   # [relu'(h0) dH0 | dGeo(layer 1)]
-            w0g = w0[:, n_ray_cols:].contiguous()
-            dz0 = D1[:, :64]
-            dw0g, _ = _layer_bwd_weight(hg[:, 64:], 128, dz0, 128, w0g, False, n)
-            if _tc_rows_ok(n):
-                _tc_bwd_data_acc(dz0, 128, w0g, D1[:, 64:], 128, n)                  # dGeo += dZ0 W0g
+            dzb = torch.empty((n, 64), **f32)
+            if ctx.needs_input_grad[0]:
+                d_enc = torch.empty((n, k_enc), **f32)
+            d_rb = torch.zeros((n_rays, 128), **f32) if d_rgb is not None else None
+            _lib.call("emer_field_bwd", _ptr(d_rgb2), _ptr(rgb), _ptr(d_sig), _ptr(sigma), _ptr(d_geo), _ptr(d_sem), _ptr(hb),
+                      _ptr(hg), _ptr(h1), _ptr(wb0), k_enc, _ptr(wb1), n_feat, _ptr(w0g), 64, _ptr(w1hg), _ptr(w1hg[:, 64:]),
+                      128, _ptr(w2), _ptr(dz2), _ptr(dz1), _ptr(D1), _ptr(dzb), _ptr(d_enc), k_enc, _ptr(d_rb), samples, n,
+                      _stream())
+            if d_rgb is not None:
+                dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n)
+                dw1hg, _ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)
+                dw0g, _ = _layer_bwd_weight(hg[:, 64:], 128, D1[:, :64], 128, w0g, False, n)
+        else:
+            # ---- layer by layer on the same buffers (ragged rays, tiny batches, EMER_CHAIN_BWD=layers)
+            if d_rgb is not None:
+                dz2 = _f32c(d_rgb.reshape(n, 3)) * (rgb * (1.0 - rgb))
+                dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n)
+                dz1 = torch.empty((n, 64), **f32)
+                _layer_bwd_data(dz2, 3, w2, dz1, 64, n, h1, 64, 64)                   # relu'(h1) applied
+                dw1hg, _ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)
+                _layer_bwd_data(dz1, 64, w1hg, D1, 128, n, hg, 128, 64)               # [relu'(h0) dH0 | dGeo(layer 1)]
+                dz0 = D1[:, :64]
+                dw0g, _ = _layer_bwd_weight(hg[:, 64:], 128, dz0, 128, w0g, False, n)
+                if _tc_rows_ok(n):
+                    _tc_bwd_data_acc(dz0, 128, w0g, D1[:, 64:], 128, n)              # dGeo += dZ0 W0g
+                else:
+                    _lib.call("emer_linear_bwd_data", _ptr(dz0), 128, None, 0, ACT_NONE, _ptr(w0g), _ptr(D1[:, 64:]), 128,
+                              n, 64, 64, 1, _stream())
+                if n_rays * samples - n:                   # ragged last ray: sum what is there
+                    d_rb = torch.zeros((n_rays, 128), **f32)
+                    d_rb[:, :64].index_add_(0, torch.arange(n, device=dev) // samples, dz0)
+                    d_rb[:, 64:].index_add_(0, torch.arange(n, device=dev) // samples, dz1)
+                else:
+                    d_rb = torch.cat([D1.view(n_rays, samples, 128)[:, :, :64].sum(1),
+                                      dz1.view(n_rays, samples, 64).sum(1)], dim=1)
             else:
-                _lib.call("emer_linear_bwd_data", _ptr(dz0), 128, None, 0, ACT_NONE, _ptr(w0g), _ptr(D1[:, 64:]), 128, n,
-                          64, 64, 1, _stream())
-            pad = n_rays * samples - n
-            if pad:                                    # ragged last ray: sum what is there
-                d_rb = torch.zeros((n_rays, 128), **f32)
-                d_rb[:, :64].index_add_(0, torch.arange(n, device=dev) // samples, dz0)
-                d_rb[:, 64:].index_add_(0, torch.arange(n, device=dev) // samples, dz1)
-            else:
-                d_rb = torch.cat([D1.view(n_rays, samples, 128)[:, :, :64].sum(1), dz1.view(n_rays, samples, 64).sum(1)],
-                                 dim=1)
+                D1[:, 64:].zero_()
+            dgeo = D1[:, 64:]
+            if d_geo is not None:
+                dgeo += d_geo
+            if d_sigma is not None:
+                # trunc_exp backward (nerf_utils.py:72-75): g * exp(clamp(x, max=15)), x = feats[:, 0] - 1 = log(sigma)
+                dgeo[:, 0] += _f32c(d_sigma).reshape(n) * torch.clamp(sigma, max=3269017.25)
+            dzb = None
+        if d_rgb is not None:
             dw0 = torch.zeros_like(w0)
             dw0[:, n_ray_cols:] = dw0g
             dw1 = torch.zeros_like(w1)
             dw1[:, :64] = dw1hg[:, :64]
             dw1[:, 64 + n_ray_cols:] = dw1hg[:, 64:]
-        else:
-            D1[:, 64:].zero_()
-        dgeo = D1[:, 64:]
-        if d_geo is not None:
-            dgeo += d_geo.reshape(n, 64)
-        if d_sigma is not None:
-            # trunc_exp backward (nerf_utils.py:72-75): g * exp(clamp(x, max=15)), x = feats[:, 0] - 1 = log(sigma)
-            dgeo[:, 0] += _f32c(d_sigma).reshape(n) * torch.clamp(sigma, max=3269017.3724721107)
         if n_feat == 128:
-            dfe = torch.cat([dgeo, torch.zeros((n, 64), **f32) if d_sem is None else _f32c(d_sem.reshape(n, 64))], dim=1)
+            dfe = torch.cat([D1[:, 64:], torch.zeros((n, 64), **f32) if d_sem is None else d_sem], dim=1)
             ldf = 128
         else:
-            dfe, ldf = dgeo, 128
+            dfe, ldf = D1[:, 64:], 128
         dwb1, dbb1 = _layer_bwd_weight(hb, 64, dfe, ldf, wb1, True, n)
-        dzb = torch.empty((n, 64), **f32)
-        _layer_bwd_data(dfe, ldf, wb1, dzb, 64, n, hb, 64, 64)
+        if dzb is None:
+            dzb = torch.empty((n, 64), **f32)
+            _layer_bwd_data(dfe, ldf, wb1, dzb, 64, n, hb, 64, 64)
+            if ctx.needs_input_grad[0]:
+                d_enc = torch.empty((n, _pad4(k_enc)), **f32)
+                _layer_bwd_data(dzb, 64, wb0, d_enc, d_enc.shape[1], n, None, 0, 0)
+                d_enc = d_enc[:, :k_enc]
         dwb0, dbb0 = _layer_bwd_weight(enc2, ld_enc, dzb, 64, wb0, True, n)
-        d_enc = None
-        if ctx.needs_input_grad[0]:
-            d_enc = torch.empty((n, _pad4(k_enc)), **f32)
-            _layer_bwd_data(dzb, 64, wb0, d_enc, d_enc.shape[1], n, None, 0, 0)
-            d_enc = d_enc[:, :k_enc].reshape(enc_shape)
+        if d_enc is not None:
+            d_enc = d_enc.reshape(enc_shape)
         return d_enc, d_rb, None, None, dwb0, dbb0, dwb1, dbb1, dw0, dw1, dw2, db2
 
 

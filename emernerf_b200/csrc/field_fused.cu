@@ -387,6 +387,410 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
     if (warp == 0) tmem_dealloc(tmem_base, 512u);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward, data path: the gradient walks the same chain, again with every intermediate in tensor memory.
+//
+//   dZ2 = d_rgb * rgb (1 - rgb)                                        (registers)
+//   s0  dH1 = dZ2 W2                 A = dZ2 [.. x 8]   B = W2^T   [64 x 8]     dZ1 = dH1 * (h1 > 0)      -> HBM, operand
+//   s1  [dH0 | dG] = dZ1 [W1h | W1g] A = dZ1            B = W1hg^T [128 x 64]   dZ0 = dH0 * (h0 > 0)      -> HBM, operand
+//   s2  dG += dZ0 W0g                A = dZ0            B = W0g^T  [64 x 64]    dF = dG + d_geo, dF[0] += d_sigma * min(sigma, e^15)
+//   s3  dHb = dF Wb1 (+ d_sem Wb1s)  A = dF (, d_sem)   B = Wb1^T  [64 x nf]    dZb = dHb * (hb > 0)      -> HBM, operand
+//   s4  d_enc = dZb Wb0              A = dZb            B = Wb0^T  [k_enc+ x 64]                          -> HBM
+//
+// dZ1, [dZ0 | dF], dZb are written out because the weight gradients (X^T dZ over ALL rows, linear_tc.cu) read them; the
+// per-ray sums of dZ0 / dZ1 -- the gradient of the per-ray bias, i.e. of the direction / embedding columns of the head --
+// are reduced here with warp shuffles (a warp = 32 consecutive samples of one ray) and added to d_ray_bias[R, 128].
+struct BwdParams {
+    const float *d_rgb, *rgb, *d_sigma, *sigma, *d_geo, *d_sem;      // [N,3] [N,3] [N] [N] [N,64]|null [N,64]|null
+    const float *hb, *hg, *h1;                                       // saved activations [N,64] [N,128] [N,64]
+    const float *wb0, *wb1; int n_feat;                              // [64, k_enc], [n_feat, 64]
+    const float* w0g; int64_t ld_w0; const float *w1h, *w1g; int64_t ld_w1; const float* w2;
+    float *dz2, *dz1, *d1, *dzb, *d_enc; int64_t ld_denc;            // [N,3], [N,64], [N,128] = [dZ0 | dF], [N,64], [N, k_enc]
+    float* d_ray_bias; int samples;                                  // [R,128] += ; ray sums only when samples % 32 == 0
+    int64_t n;
+};
+
+struct BSmem {
+    int w2_hi, w2_lo, w1_hi, w1_lo, w0_hi, w0_lo, wb1_hi, wb1_lo, wb0_hi, wb0_lo, bars, total;
+};
+__host__ __device__ inline BSmem bsmem_map(int k_enc, int n_feat) {
+    BSmem m;
+    int o = 0;
+    const int kpad = (k_enc + 15) / 16 * 16;                         // N of the last product: a multiple of 16
+    const int w2 = (8 / 4) * H * 16, w1 = (H / 4) * 128 * 16, w0 = (H / 4) * H * 16, wb1 = (n_feat / 4) * H * 16,
+              wb0 = (H / 4) * kpad * 16;
+    m.w2_hi = o; o += w2; m.w2_lo = o; o += w2;
+    m.w1_hi = o; o += w1; m.w1_lo = o; o += w1;
+    m.w0_hi = o; o += w0; m.w0_lo = o; o += w0;
+    m.wb1_hi = o; o += wb1; m.wb1_lo = o; o += wb1;
+    m.wb0_hi = o; o += wb0; m.wb0_lo = o; o += wb0;
+    m.bars = o; o += 8 * 8;
+    m.total = o;
+    return m;
+}
+
+// B = W^T for a data gradient: operand row j (input feature), reduction index o (output feature): element w[o, j]
+__device__ __forceinline__ void stage_weight_t(uint8_t* hi, uint8_t* lo, const float* __restrict__ w, int64_t ld, int rows,
+                                               int rows_valid, int kpad, int k_valid, int row0, int k0, int tid,
+                                               int nthreads) {
+    const int panel = rows * 16;
+    for (int e = tid; e < rows_valid * k_valid; e += nthreads) {
+        const int o = e / rows_valid, j = e - o * rows_valid;        // consecutive threads: consecutive j (coalesced)
+        float h, l;
+        split(__ldg(w + (int64_t)o * ld + j), h, l);
+        const int k = k0 + o;
+        const int off = (k >> 2) * panel + (row0 + j) * 16 + (k & 3) * 4;
+        *reinterpret_cast<float*>(hi + off) = h;
+        *reinterpret_cast<float*>(lo + off) = l;
+    }
+    (void)kpad;
+}
+
+// bit j of the result: x[j] > 0 for the 64 floats of one saved activation row
+__device__ __forceinline__ uint64_t relu_mask64(const float* __restrict__ row, bool ok) {
+    uint64_t m = 0;
+    if (ok) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(row) + q);
+            m |= (uint64_t)((t.x > 0.f) | ((t.y > 0.f) << 1) | ((t.z > 0.f) << 2) | ((t.w > 0.f) << 3)) << (4 * q);
+        }
+    }
+    return m;
+}
+
+// Column sums over the 32 lanes of a warp of v[16] (recursive halving: 15 + 1 shuffles).  Afterwards every lane holds the
+// total of ONE column: col = 8 b4 + 4 b3 + 2 b2 + b1 of its lane index (lanes l and l ^ 1 hold the same column).
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane, int& col) {
+    float a[8];
+    const bool b4 = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float send = b4 ? v[j] : v[j + 8];
+        const float keep = b4 ? v[j + 8] : v[j];
+        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float b[4];
+    const bool b3 = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float send = b3 ? a[j] : a[j + 4];
+        const float keep = b3 ? a[j + 4] : a[j];
+        b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float c[2];
+    const bool b2 = lane & 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = b2 ? b[j] : b[j + 2];
+        const float keep = b2 ? b[j + 2] : b[j];
+        c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const bool b1 = lane & 2;
+    float d = (b1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, b1 ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    col = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+    return d;
+}
+
+template <int K_ENC>
+__global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int KPAD = (K_ENC + 15) / 16 * 16;
+    const BSmem m = bsmem_map(K_ENC, p.n_feat);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + m.bars);
+    uint64_t* a_full = bars;
+    uint64_t* d_full = bars + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const bool is_issuer = warp == EPI_THREADS / 32;
+
+    if (tid == 0) {
+        mbar_init(&a_full[0], ROWS);
+        mbar_init(&a_full[1], ROWS);
+        mbar_init(&d_full[0], 1);
+        mbar_init(&d_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512u);
+    }
+    for (int i = tid * 16; i < m.bars; i += THREADS * 16) *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    stage_weight_t(smem + m.w2_hi, smem + m.w2_lo, p.w2, H, H, H, 8, 3, 0, 0, tid, THREADS);                 // [64 x 8]
+    stage_weight_t(smem + m.w1_hi, smem + m.w1_lo, p.w1h, p.ld_w1, 128, H, H, H, 0, 0, tid, THREADS);       // rows 0..63
+    stage_weight_t(smem + m.w1_hi, smem + m.w1_lo, p.w1g, p.ld_w1, 128, H, H, H, H, 0, tid, THREADS);       // rows 64..127
+    stage_weight_t(smem + m.w0_hi, smem + m.w0_lo, p.w0g, p.ld_w0, H, H, H, H, 0, 0, tid, THREADS);
+    stage_weight_t(smem + m.wb1_hi, smem + m.wb1_lo, p.wb1, H, H, H, p.n_feat, p.n_feat, 0, 0, tid, THREADS);  // [64 x nf]
+    stage_weight_t(smem + m.wb0_hi, smem + m.wb0_lo, p.wb0, K_ENC, KPAD, K_ENC, H, H, 0, 0, tid, THREADS);  // [kpad x 64]
+    fence_async_proxy();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t n_tiles = (p.n + ROWS - 1) / ROWS;
+    const int64_t pair_stride = (int64_t)gridDim.x * 2;
+    const int iters = (int)((n_tiles + pair_stride - 1) / pair_stride);
+    const int n_stages = p.n_feat > H ? 6 : 5;           // (with a semantic half, stage 3 takes its operand in two pieces)
+
+    if (is_issuer) {
+        const uint32_t sbase = smem_u32(smem);
+        const uint64_t d64 = make_desc(0, H * 16, 128), d128 = make_desc(0, 128 * 16, 128), dkp = make_desc(0, KPAD * 16, 128);
+        const uint32_t id64 = make_idesc(128, 64), id128 = make_idesc(128, 128), idkp = make_idesc(128, KPAD);
+        uint32_t ph[2] = {0, 0};
+        for (int it = 0; it < iters; ++it) {
+            for (int st = 0; st < n_stages; ++st) {
+                // stage ids: 0 dZ2 W2 | 1 dZ1 W1hg | 2 dZ0 W0g | 3 dF Wb1 | (5: d_sem Wb1[:, 64:]) | 4 dZb Wb0
+                const int stage = (n_stages == 6) ? (st < 4 ? st : (st == 4 ? 5 : 4)) : st;
+                for (int wg = 0; wg < 2; ++wg) {
+                    const int64_t tile = ((int64_t)it * gridDim.x + blockIdx.x) * 2 + wg;
+                    if (tile >= n_tiles) continue;
+                    mbar_wait(&a_full[wg], ph[wg]);
+                    ph[wg] ^= 1u;
+                    tc_fence_after();
+                    if (mma_issue_lane(tid)) {
+                        const uint32_t a_hi = tmem_base + (uint32_t)(wg * 256);
+                        const uint32_t a_lo = a_hi + 64u;
+                        uint32_t d = a_hi + 128u;
+                        uint64_t desc = d64;
+                        uint32_t idesc = id64, b_hi, b_lo, panel = H * 16, acc0 = 0u, koff = 0u;
+                        int ksteps = H / 8;
+                        if (stage == 0) { b_hi = m.w2_hi; b_lo = m.w2_lo; ksteps = 1; }
+                        else if (stage == 1) { desc = d128; idesc = id128; b_hi = m.w1_hi; b_lo = m.w1_lo; panel = 128 * 16; }
+                        else if (stage == 2) { b_hi = m.w0_hi; b_lo = m.w0_lo; d += 64u; acc0 = 1u; }
+                        else if (stage == 3) { b_hi = m.wb1_hi; b_lo = m.wb1_lo; }
+                        else if (stage == 5) { b_hi = m.wb1_hi; b_lo = m.wb1_lo; acc0 = 1u; koff = (uint32_t)(16 * panel) >> 4; }
+                        else { desc = dkp; idesc = idkp; b_hi = m.wb0_hi; b_lo = m.wb0_lo; panel = KPAD * 16; }
+                        const uint32_t bh = ((sbase + b_hi) >> 4) + koff, bl = ((sbase + b_lo) >> 4) + koff;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t bo = (uint32_t)(ks * 2 * panel) >> 4;
+                            const uint64_t db_hi = desc | (uint64_t)(bh + bo), db_lo = desc | (uint64_t)(bl + bo);
+                            const uint32_t ah = a_hi + (uint32_t)(ks * 8), al = a_lo + (uint32_t)(ks * 8);
+                            mma_tf32_ts(d, ah, db_hi, idesc, (ks > 0) ? 1u : acc0);
+                            mma_tf32_ts(d, al, db_hi, idesc, 1u);
+                            mma_tf32_ts(d, ah, db_lo, idesc, 1u);
+                        }
+                        tc_commit(&d_full[wg]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int wg = tid >> 7;
+        const int r_in = tid & 127;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(wg * 256);
+        const uint32_t a_lo = a_hi + 64u;
+        const uint32_t d_addr = a_hi + 128u;
+        const bool ray_sums = p.d_ray_bias != nullptr && (p.samples % 32 == 0);
+        uint32_t ph = 0;
+
+        for (int it = 0; it < iters; ++it) {
+            const int64_t tile = ((int64_t)it * gridDim.x + blockIdx.x) * 2 + wg;
+            if (tile >= n_tiles) break;
+            const int64_t row = tile * ROWS + r_in;
+            const bool row_ok = row < p.n;
+            const int64_t rsafe = row_ok ? row : 0;
+            // the warp's 32 rows belong to one ray (samples % 32 == 0); rows past the end contribute zeros
+            const int64_t ray = (tile * ROWS + (r_in & ~31)) / p.samples;
+            const bool warp_live = tile * ROWS + (r_in & ~31) < p.n;
+
+            // ---- stage 0 operand: dZ2 = d_rgb * rgb (1 - rgb), 3 columns of an 8-wide k step
+            {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hi[j] = lo[j] = 0u;
+                if (row_ok && p.d_rgb) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float y = __ldg(p.rgb + row * 3 + j);
+                        const float g = __ldg(p.d_rgb + row * 3 + j) * (y * (1.0f - y));
+                        if (p.dz2) p.dz2[row * 3 + j] = g;
+                        float h, l;
+                        split(g, h, l);
+                        hi[j] = __float_as_uint(h);
+                        lo[j] = __float_as_uint(l);
+                    }
+                }
+                tmem_st8(a_hi, hi);
+                tmem_st8(a_lo, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 0 result: dZ1 = dH1 * (h1 > 0)
+            uint64_t mask = relu_mask64(p.h1 + rsafe * H, row_ok);
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + (uint32_t)(c * 16), r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c * 16 + j)) & 1ull) ? __uint_as_float(r[j]) : 0.0f;
+                if (row_ok) store16(p.dz1 + row * H + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+                if (ray_sums) {
+                    int col;
+                    const float sum = warp_colsum16(v, lane, col);
+                    if (!(lane & 1) && warp_live) atomicAdd(p.d_ray_bias + ray * 128 + H + c * 16 + col, sum);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 1 result: dZ0 = dH0 * (h0 > 0)   (dG stays in the accumulator's upper half)
+            mask = relu_mask64(p.hg + rsafe * 128, row_ok);
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + (uint32_t)(c * 16), r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c * 16 + j)) & 1ull) ? __uint_as_float(r[j]) : 0.0f;
+                if (row_ok) store16(p.d1 + row * 128 + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+                if (ray_sums) {
+                    int col;
+                    const float sum = warp_colsum16(v, lane, col);
+                    if (!(lane & 1) && warp_live) atomicAdd(p.d_ray_bias + ray * 128 + c * 16 + col, sum);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 2 result: dF = dG (+ d_geo); dF[0] += d_sigma * exp(min(x, 15)), exp(x) = sigma (nerf_utils.py:72-75)
+            float ds = 0.0f;
+            if (row_ok && p.d_sigma) ds = __ldg(p.d_sigma + row) * fminf(__ldg(p.sigma + row), 3269017.25f);
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + 64u + (uint32_t)(c * 16), r);
+                float g[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) g[j] = 0.0f;
+                if (p.d_geo && row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.d_geo + row * H + c * 16 + j));
+                        g[j] = t.x; g[j + 1] = t.y; g[j + 2] = t.z; g[j + 3] = t.w;
+                    }
+                }
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + g[j];
+                if (c == 0) v[0] += ds;
+                if (row_ok) store16(p.d1 + row * 128 + H + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            if (p.n_feat > H) {
+                // ---- second operand piece of stage 3: the gradient of the semantic half
+                mbar_wait(&d_full[wg], ph); ph ^= 1u;           // (the first piece's MMAs have read the operand)
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+                    if (p.d_sem && row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.d_sem + row * H + c * 16 + j));
+                            v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+                        }
+                    }
+                    uint32_t hi[16], lo[16];
+                    split16(v, hi, lo);
+                    tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                    tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&a_full[wg]);
+            }
+
+            // ---- stage 3 result: dZb = dHb * (hb > 0)
+            mask = relu_mask64(p.hb + rsafe * H, row_ok);
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[16];
+                tmem_ld16(d_addr + (uint32_t)(c * 16), r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c * 16 + j)) & 1ull) ? __uint_as_float(r[j]) : 0.0f;
+                if (row_ok) store16(p.dzb + row * H + c * 16, v);
+                uint32_t hi[16], lo[16];
+                split16(v, hi, lo);
+                tmem_st16(a_hi + (uint32_t)(c * 16), hi);
+                tmem_st16(a_lo + (uint32_t)(c * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[wg]);
+
+            // ---- stage 4 result: d_enc
+            mbar_wait(&d_full[wg], ph); ph ^= 1u;
+            tc_fence_after();
+            if (p.d_enc) {
+#pragma unroll
+                for (int c = 0; c < K_ENC / 8; ++c) {
+                    uint32_t r[8];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                                 : "r"(d_addr + (uint32_t)(c * 8))
+                                 : "memory");
+                    tmem_ld_wait();
+                    if (row_ok) {
+                        float* dst = p.d_enc + row * p.ld_denc + c * 8;
+                        *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]),
+                                                                      __uint_as_float(r[2]), __uint_as_float(r[3]));
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]),
+                                                                          __uint_as_float(r[6]), __uint_as_float(r[7]));
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512u);
+}
+
 }  // namespace ff
 }  // namespace emer
 
@@ -440,4 +844,56 @@ extern "C" int emer_field_fwd(const float* enc, int64_t ld_enc, int k_enc, const
     else rc = launch(field_fwd_kernel<64>, configured_dev[2][dev]);
     if (rc) return rc;
     return check_launch("emer_field_fwd");
+}
+
+extern "C" int emer_field_bwd(const float* d_rgb, const float* rgb, const float* d_sigma, const float* sigma,
+                              const float* d_geo, const float* d_sem, const float* hb, const float* hg, const float* h1,
+                              const float* wb0, int k_enc, const float* wb1, int n_feat, const float* w0g, int64_t ld_w0,
+                              const float* w1h, const float* w1g, int64_t ld_w1, const float* w2, float* dz2, float* dz1,
+                              float* d1, float* dzb, float* d_enc, int64_t ld_denc, float* d_ray_bias, int samples,
+                              int64_t n, void* stream) {
+    using namespace emer::ff;
+    if (n == 0) return 0;
+    EMER_REQUIRE(rgb && sigma && hb && hg && h1 && wb0 && wb1 && w0g && w1h && w1g && w2 && dz1 && d1 && dzb,
+                 "emer_field_bwd: NULL pointer");
+    EMER_REQUIRE(k_enc == 32 || k_enc == 40 || k_enc == 64, "emer_field_bwd: k_enc=%d must be 32, 40 or 64", k_enc);
+    EMER_REQUIRE(n_feat == 64 || n_feat == 128, "emer_field_bwd: n_feat=%d must be 64 or 128", n_feat);
+    EMER_REQUIRE(samples > 0, "emer_field_bwd: samples per ray must be positive");
+    EMER_REQUIRE(!d_enc || (ld_denc % 4 == 0 && ld_denc >= k_enc), "emer_field_bwd: d_enc rows must be 16-byte aligned");
+    EMER_REQUIRE((((uintptr_t)hb | (uintptr_t)hg | (uintptr_t)h1 | (uintptr_t)dz1 | (uintptr_t)d1 | (uintptr_t)dzb |
+                   (uintptr_t)d_enc | (uintptr_t)d_geo | (uintptr_t)d_sem) & 15) == 0,
+                 "emer_field_bwd: row buffers must be 16-byte aligned");
+    EMER_REQUIRE(!d_ray_bias || samples % 32 == 0, "emer_field_bwd: per-ray sums need samples %% 32 == 0 (got %d)", samples);
+    BwdParams p{};
+    p.d_rgb = d_rgb; p.rgb = rgb; p.d_sigma = d_sigma; p.sigma = sigma; p.d_geo = d_geo; p.d_sem = d_sem;
+    p.hb = hb; p.hg = hg; p.h1 = h1; p.wb0 = wb0; p.wb1 = wb1; p.n_feat = n_feat;
+    p.w0g = w0g; p.ld_w0 = ld_w0; p.w1h = w1h; p.w1g = w1g; p.ld_w1 = ld_w1; p.w2 = w2;
+    p.dz2 = dz2; p.dz1 = dz1; p.d1 = d1; p.dzb = dzb; p.d_enc = d_enc; p.ld_denc = ld_denc; p.d_ray_bias = d_ray_bias; p.samples = samples;
+    p.n = n;
+    const BSmem m = bsmem_map(k_enc, n_feat);
+    const size_t smem = (size_t)m.total;
+    EMER_REQUIRE(smem <= 227 * 1024, "emer_field_bwd: %zu B of shared memory needed", smem);
+    const int64_t n_tiles = ceil_div(n, ROWS);
+    int64_t grid = sm_count();
+    if (grid > ceil_div(n_tiles, 2)) grid = ceil_div(n_tiles, 2);
+    auto launch = [&](auto kernel, size_t& configured) -> int {
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                set_error("emer_field_bwd: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+                return -2;
+            }
+            configured = smem;
+        }
+        kernel<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+        return 0;
+    };
+    static size_t configured_dev[3][64] = {{0}};
+    const int dev = current_device();
+    int rc;
+    if (k_enc == 32) rc = launch(field_bwd_kernel<32>, configured_dev[0][dev]);
+    else if (k_enc == 40) rc = launch(field_bwd_kernel<40>, configured_dev[1][dev]);
+    else rc = launch(field_bwd_kernel<64>, configured_dev[2][dev]);
+    if (rc) return rc;
+    return check_launch("emer_field_bwd");
 }

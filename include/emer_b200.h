@@ -178,6 +178,21 @@ int emer_field_fwd(const float* enc, int64_t ld_enc, int k_enc, const float* wb0
                    const float* ray_bias, int samples, float* sigma, float* rgb, float* save_hb, float* save_hg,
                    float* save_h1, float* save_sem, int64_t n, void* stream);
 
+/* Backward of emer_field_fwd, data path (the autograd graph of the same reference lines), one kernel, every
+ * intermediate gradient in tensor memory:
+ *   dz2[N,3] = d_rgb * rgb (1 - rgb);  dz1[N,64] = (dz2 w2) * (h1 > 0);
+ *   d1[N,128] = [dz0 | dF]: dz0 = (dz1 w1h) * (h0 > 0), dF = dz1 w1g + dz0 w0g + d_geo, dF[:,0] += d_sigma * min(sigma, e^15)
+ *   dzb[N,64] = (dF wb1[:64] + d_sem wb1[64:]) * (hb > 0);  d_enc[N, k_enc] = dzb wb0   (row stride ld_denc)
+ *   d_ray_bias[R,128] += per-ray sums of [dz0 | dz1]   (caller zeroes; needs samples % 32 == 0; may be NULL)
+ * hb / hg / h1 / rgb / sigma are emer_field_fwd's saves and outputs.  d_rgb, d_sigma, d_geo, d_sem, d_enc, dz2 may be
+ * NULL.  The weight gradients are X^T dZ products over dz2 / dz1 / d1 / dzb (emer_linear_tc_bwd_weight). */
+int emer_field_bwd(const float* d_rgb, const float* rgb, const float* d_sigma, const float* sigma,
+                   const float* d_geo, const float* d_sem, const float* hb, const float* hg, const float* h1,
+                   const float* wb0, int k_enc, const float* wb1, int n_feat, const float* w0g, int64_t ld_w0,
+                   const float* w1h, const float* w1g, int64_t ld_w1, const float* w2, float* dz2, float* dz1,
+                   float* d1, float* dzb, float* d_enc, int64_t ld_denc, float* d_ray_bias, int samples,
+                   int64_t n, void* stream);
+
 /* ---- volume rendering along rays (replaces nerfacc.render_transmittance_from_density /
  *      render_weight_from_density / accumulate_along_rays and the torch cumsum/searchsorted of
  *      radiance_fields/render_utils.py:73-115) ---------------------------------------------- */

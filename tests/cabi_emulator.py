@@ -454,6 +454,49 @@ def emer_field_fwd(enc, ld_enc, k_enc, wb0, bb0, wb1, bb1, n_feat, w0g, ld_w0, w
             _view(save_sem, n, 64).copy_(feats[:, 64:])
 
 
+def emer_field_bwd(d_rgb, rgb, d_sigma, sigma, d_geo, d_sem, hb, hg, h1, wb0, k_enc, wb1, n_feat, w0g, ld_w0, w1h, w1g,
+                   ld_w1, w2, dz2, dz1, d1, dzb, d_enc, ld_denc, d_ray_bias, samples, n, stream):
+    _require(k_enc in (32, 40, 64) and n_feat in (64, 128) and samples > 0, "emer_field_bwd: bad shape")
+    _require(not _addr(d_enc) or (ld_denc % 4 == 0 and ld_denc >= k_enc), "emer_field_bwd: d_enc rows must be 16-byte aligned")
+    _require(_aligned16(hb, hg, h1, dz1, d1, dzb, d_enc, d_geo, d_sem), "emer_field_bwd: row buffers must be 16-byte aligned")
+    _require(not _addr(d_ray_bias) or samples % 32 == 0, "emer_field_bwd: per-ray sums need samples % 32 == 0")
+    if n == 0:
+        return
+    with torch.no_grad():
+        z2 = torch.zeros(n, 3)
+        if _addr(d_rgb):
+            y = _view(rgb, n, 3)
+            z2 = _view(d_rgb, n, 3) * (y * (1.0 - y))
+        if _addr(dz2):
+            _view(dz2, n, 3).copy_(z2)
+        z1 = (z2 @ _view(w2, 3, 64)) * (_view(h1, n, 64) > 0)
+        _view(dz1, n, 64).copy_(z1)
+        h0 = _view(hg, n, 64, 128)
+        z0 = (z1 @ _view(w1h, 64, 64, ld_w1)) * (h0 > 0)
+        dF = z1 @ _view(w1g, 64, 64, ld_w1) + z0 @ _view(w0g, 64, 64, ld_w0)
+        if _addr(d_geo):
+            dF = dF + _view(d_geo, n, 64)
+        if _addr(d_sigma):
+            dF[:, 0] += _vec(d_sigma, n) * torch.clamp(_vec(sigma, n), max=3269017.25)
+        out = _view(d1, n, 128)
+        out[:, :64] = z0
+        out[:, 64:] = dF
+        wb1_ = _view(wb1, n_feat, 64)
+        dhb = dF @ wb1_[:64]
+        if n_feat == 128 and _addr(d_sem):
+            dhb = dhb + _view(d_sem, n, 64) @ wb1_[64:]
+        zb = dhb * (_view(hb, n, 64) > 0)
+        _view(dzb, n, 64).copy_(zb)
+        if _addr(d_enc):
+            _view(d_enc, n, k_enc, ld_denc).copy_(zb @ _view(wb0, 64, k_enc))
+        if _addr(d_ray_bias):
+            n_rays = (n + samples - 1) // samples
+            acc = _view(d_ray_bias, n_rays, 128)
+            ray = torch.arange(n) // samples
+            acc[:, :64].index_add_(0, ray, z0)
+            acc[:, 64:].index_add_(0, ray, z1)
+
+
 # ----------------------------------------------------------------------------- dispatch
 def call(name: str, *args) -> None:
     """Stand-in for ``emernerf_b200._lib.call``: same names, same positional arguments."""
