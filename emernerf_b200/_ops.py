@@ -8,7 +8,8 @@ tensors must live on a CUDA device -- there is no CPU path.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Sequence, Tuple
+import weakref
+from typing import Callable, Dict, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -62,6 +63,41 @@ def _need_cuda(*ts: Tensor) -> None:
         _lib.DEVICE = dev
 
 
+# ----------------------------------------------------------------------------- gradient sinks
+# ``emernerf_b200.optim.FusedAdam`` owns one persistent, pre-zeroed flat gradient buffer per parameter group and
+# registers every parameter's slice here.  A library backward that produces a parameter gradient looks its parameter
+# up (by storage address) and ACCUMULATES into the slice -- the scatter / weight-gradient kernels add with atomics anyway
+# -- instead of allocating and zero-filling a fresh tensor that autograd would then copy or add: for the 122 MB hash
+# table that is a 122 MB memset per backward.  It returns None for that input (autograd has nothing left to do) and
+# tells the optimizer the parameter was touched.  Without a registered sink (the reference's own torch.optim.Adam) the
+# ordinary autograd path runs.
+_GRAD_SINKS: Dict[int, Tuple[Tensor, Callable, "weakref.ref"]] = {}
+
+
+def register_grad_sink(param: Tensor, sink: Tensor, on_touch: Callable) -> None:
+    if sink.shape != param.shape or sink.dtype != torch.float32 or not sink.is_contiguous():
+        raise ValueError("grad sink must be a contiguous fp32 tensor of the parameter's shape")
+    _GRAD_SINKS[param.data_ptr()] = (sink, on_touch, weakref.ref(param))
+
+
+def clear_grad_sinks() -> None:
+    _GRAD_SINKS.clear()
+
+
+def _grad_sink(t: Optional[Tensor]):
+    """(sink, touch) for a registered parameter's storage, else None."""
+    if t is None or not _GRAD_SINKS:
+        return None
+    e = _GRAD_SINKS.get(t.data_ptr())
+    if e is None:
+        return None
+    sink, on_touch, ref = e
+    p = ref()
+    if p is None or p.data_ptr() != t.data_ptr() or sink.shape != t.shape:
+        return None
+    return sink, (lambda: on_touch(p))
+
+
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
         t = t.to(torch.float32)
@@ -101,11 +137,18 @@ class _GridEncode(torch.autograd.Function):
         desc = ctx.desc
         dy = _f32c(dy)
         need_x, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dparams = torch.zeros_like(params) if need_p else None
+        sink = _grad_sink(params) if need_p else None
+        if sink is not None:
+            dparams = sink[0]                     # the optimizer's pre-zeroed slice: scatter straight into it
+        else:
+            dparams = torch.zeros_like(params) if need_p else None
         dx = torch.empty_like(x) if need_x else None
         if need_x or need_p:
             _lib.call("emer_grid_bwd", ctypes.byref(desc.c), _ptr(x), _ptr(params), _ptr(dy), _ptr(dparams),
                       _ptr(dx), x.shape[0], _stream())
+        if sink is not None:
+            sink[1]()
+            dparams = None
         return dx, dparams, None
 
 
@@ -281,10 +324,18 @@ def _layer_bwd_data(dz: Tensor, lddz: int, w: Tensor, dx: Tensor, lddx: int, n: 
             dx[:, :relu_cols].mul_(relu_src[:, :relu_cols] > 0)
 
 
-def _layer_bwd_weight(x2: Tensor, ldx: int, dz: Tensor, lddz: int, w: Tensor, has_bias: bool, n: int):
+def _layer_bwd_weight(x2: Tensor, ldx: int, dz: Tensor, lddz: int, w: Tensor, has_bias: bool, n: int,
+                      w_sink=None, b_sink=None):
+    """(dW, db) of one layer.  With gradient sinks (``_grad_sink`` of the weight / bias parameter) the kernels
+    accumulate into the optimizer's buffers and the returned entries are None."""
     n_out, k = w.shape
-    dw = torch.zeros_like(w)
-    db = torch.zeros(n_out, dtype=torch.float32, device=w.device) if has_bias else None
+    dw = w_sink[0] if w_sink is not None else torch.zeros_like(w)
+    if not has_bias:
+        db = None
+    elif b_sink is not None:
+        db = b_sink[0]
+    else:
+        db = torch.zeros(n_out, dtype=torch.float32, device=w.device)
     tc = (_tc_rows_ok(n) and LINEAR_WGRAD_IMPL == "tc" and _tc_wgrad_fits(k, n_out) and n_out % 4 == 0
           and _aligned(x2, ldx) and _aligned(dz, lddz) and _pad4(k) <= ldx)
     if _narrow_ok(k, n_out):
@@ -296,6 +347,12 @@ def _layer_bwd_weight(x2: Tensor, ldx: int, dz: Tensor, lddz: int, w: Tensor, ha
     else:
         _lib.call("emer_linear_bwd_weight", _ptr(x2), ldx, _ptr(dz), lddz, None, 0, ACT_NONE, _ptr(dw), _ptr(db), n, k,
                   n_out, _stream())
+    if w_sink is not None:
+        w_sink[1]()
+        dw = None
+    if has_bias and b_sink is not None:
+        b_sink[1]()
+        db = None
     return dw, db
 
 
@@ -314,6 +371,7 @@ class _MLPChain(torch.autograd.Function):
         ws = [_f32c(w) for w in (params[0::2] if has_bias else params)]
         bs = [_f32c(b) for b in params[1::2]] if has_bias else [None] * len(ws)
         _need_cuda(x, *ws)
+        ctx.sinks = [(_grad_sink(w), _grad_sink(b)) for w, b in zip(ws, bs)]
         k0 = ws[0].shape[1]
         lead = x.shape[:-1]
         x2, ldx = _rows(x, k0)
@@ -396,7 +454,7 @@ class _MLPChain(torch.autograd.Function):
             inp, ld = inputs[i], lds[i]
             w_idx = _CHAIN_ARGS + (2 * i if has_bias else i)
             if ctx.needs_input_grad[w_idx] or (has_bias and ctx.needs_input_grad[w_idx + 1]):
-                grads_w[i], grads_b[i] = _layer_bwd_weight(inp, ld, dz, lddz, w, has_bias, n)
+                grads_w[i], grads_b[i] = _layer_bwd_weight(inp, ld, dz, lddz, w, has_bias, n, *ctx.sinks[i])
             if i == 0 and not need_x:
                 break
             if stacked and i == 2:
@@ -595,6 +653,7 @@ class _FieldChain(torch.autograd.Function):
                   _ptr(sigma), _ptr(rgb), _ptr(hb), _ptr(hg), _ptr(h1), _ptr(sem), n, _stream())
         geo = hg[:, 64:] if want_geo else None
         if train:
+            ctx.sinks = {k: _grad_sink(t) for k, t in zip(("wb0", "bb0", "wb1", "bb1", "w0", "w1", "w2", "b2"), ws)}
             ctx.save_for_backward(enc2, hb, hg, h1, rgb, sigma, wb0c, wb1c, w0c, w1c, w2c)
             ctx.meta = (samples, n_ray_cols, n_feat, enc.shape, ld_enc)
         return sigma, rgb, geo, sem
@@ -610,6 +669,7 @@ class _FieldChain(torch.autograd.Function):
         if d_sigma is None and d_rgb is None and d_geo is None and d_sem is None:
             return none
         n_rays = (n + samples - 1) // samples
+        sk = ctx.sinks
         w1hg = torch.cat([w1[:, :64], w1[:, 64 + n_ray_cols:]], dim=1)            # [64, 128] = [hidden | geo] columns
         w0g = w0[:, n_ray_cols:].contiguous()
         D1 = torch.empty((n, 128), **f32)          # [dZ0 | dF] side by side (row stride 128)
@@ -631,14 +691,14 @@ class _FieldChain(torch.autograd.Function):
                       128, _ptr(w2), _ptr(dz2), _ptr(dz1), _ptr(D1), _ptr(dzb), _ptr(d_enc), k_enc, _ptr(d_rb), samples, n,
                       _stream())
             if d_rgb is not None:
-                dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n)
+                dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n, sk["w2"], sk["b2"])
                 dw1hg, _ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)
                 dw0g, _ = _layer_bwd_weight(hg[:, 64:], 128, D1[:, :64], 128, w0g, False, n)
         else:
             # ---- layer by layer on the same buffers (ragged rays, tiny batches, EMER_CHAIN_BWD=layers)
             if d_rgb is not None:
                 dz2 = _f32c(d_rgb.reshape(n, 3)) * (rgb * (1.0 - rgb))
-                dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n)
+                dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n, sk["w2"], sk["b2"])
                 dz1 = torch.empty((n, 64), **f32)
                 _layer_bwd_data(dz2, 3, w2, dz1, 64, n, h1, 64, 64)                   # relu'(h1) applied
                 dw1hg, _ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)
@@ -667,17 +727,27 @@ class _FieldChain(torch.autograd.Function):
                 dgeo[:, 0] += _f32c(d_sigma).reshape(n) * torch.clamp(sigma, max=3269017.25)
             dzb = None
         if d_rgb is not None:
-            dw0 = torch.zeros_like(w0)
-            dw0[:, n_ray_cols:] = dw0g
-            dw1 = torch.zeros_like(w1)
-            dw1[:, :64] = dw1hg[:, :64]
-            dw1[:, 64 + n_ray_cols:] = dw1hg[:, 64:]
+            # the head's geo / hidden column blocks; its per-ray columns get their gradient through ray_bias
+            if sk["w0"] is not None:
+                sk["w0"][0][:, n_ray_cols:] += dw0g
+                sk["w0"][1]()
+            else:
+                dw0 = torch.zeros_like(w0)
+                dw0[:, n_ray_cols:] = dw0g
+            if sk["w1"] is not None:
+                sk["w1"][0][:, :64] += dw1hg[:, :64]
+                sk["w1"][0][:, 64 + n_ray_cols:] += dw1hg[:, 64:]
+                sk["w1"][1]()
+            else:
+                dw1 = torch.zeros_like(w1)
+                dw1[:, :64] = dw1hg[:, :64]
+                dw1[:, 64 + n_ray_cols:] = dw1hg[:, 64:]
         if n_feat == 128:
             dfe = torch.cat([D1[:, 64:], torch.zeros((n, 64), **f32) if d_sem is None else d_sem], dim=1)
             ldf = 128
         else:
             dfe, ldf = D1[:, 64:], 128
-        dwb1, dbb1 = _layer_bwd_weight(hb, 64, dfe, ldf, wb1, True, n)
+        dwb1, dbb1 = _layer_bwd_weight(hb, 64, dfe, ldf, wb1, True, n, sk["wb1"], sk["bb1"])
         if dzb is None:
             dzb = torch.empty((n, 64), **f32)
             _layer_bwd_data(dfe, ldf, wb1, dzb, 64, n, hb, 64, 64)
@@ -685,7 +755,7 @@ class _FieldChain(torch.autograd.Function):
                 d_enc = torch.empty((n, _pad4(k_enc)), **f32)
                 _layer_bwd_data(dzb, 64, wb0, d_enc, d_enc.shape[1], n, None, 0, 0)
                 d_enc = d_enc[:, :k_enc]
-        dwb0, dbb0 = _layer_bwd_weight(enc2, ld_enc, dzb, 64, wb0, True, n)
+        dwb0, dbb0 = _layer_bwd_weight(enc2, ld_enc, dzb, 64, wb0, True, n, sk["wb0"], sk["bb0"])
         if d_enc is not None:
             d_enc = d_enc.reshape(enc_shape)
         return d_enc, d_rb, None, None, dwb0, dbb0, dwb1, dbb1, dw0, dw1, dw2, db2

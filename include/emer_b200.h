@@ -213,6 +213,24 @@ int emer_accumulate_fwd(const float* w, const float* v, float* out, int64_t n_ra
 int emer_accumulate_bwd(const float* w, const float* v, const float* g, float* dw, float* dv,
                         int64_t n_rays, int n_samples, int c, void* stream);
 
+/* ---- optimizer (replaces torch.optim.Adam's step + optimizer.zero_grad() + tiny-cuda-nn's gradient memset,
+ *      builders.py:50-61,114-120; train_emernerf.py:742-745,823-826) --------------------------------------------- */
+/* One parameter block: n fp32 values of a parameter, its gradient and Adam moments (16-byte aligned, device). */
+typedef struct emer_adam_block {
+    float* param;
+    float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n;
+} emer_adam_block;
+/* Adam (amsgrad = False) over n_blocks blocks in ONE launch; the consumed gradient is zeroed when zero_grad != 0.
+ * blocks / prefix are DEVICE arrays: block b covers the virtual index range [prefix[b], prefix[b+1]) (prefix[b]
+ * multiples of 4, prefix[n_blocks] = total).  hyper = device {step (already incremented), lr}: read at run time so
+ * that a captured CUDA graph replays with the live values. */
+int emer_adam_step(const emer_adam_block* blocks, const int64_t* prefix, int n_blocks, int64_t total,
+                   const float* hyper, float beta1, float beta2, float eps, float weight_decay, int zero_grad,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -497,6 +497,26 @@ def emer_field_bwd(d_rgb, rgb, d_sigma, sigma, d_geo, d_sem, hb, hg, h1, wb0, k_
             acc[:, 64:].index_add_(0, ray, z1)
 
 
+# ----------------------------------------------------------------------------- optimizer
+def emer_adam_step(blocks, prefix, n_blocks, total, hyper, beta1, beta2, eps, weight_decay, zero_grad, stream):
+    if n_blocks == 0 or total == 0:
+        return
+    rows = _view(blocks, n_blocks, 5, ctype=ctypes.c_int64, dtype=np.int64)
+    step, lr = [float(v) for v in _vec(hyper, 2)]
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    with torch.no_grad():
+        for r in rows.tolist():
+            n = r[4]
+            p, g, m, v = (_vec(a, n) for a in r[:4])
+            _require(all(a % 16 == 0 for a in r[:4]), "emer_adam_step: blocks must be 16-byte aligned")
+            gg = g + weight_decay * p if weight_decay != 0 else g.clone()
+            m.add_((1.0 - beta1) * (gg - m))
+            v.mul_(beta2).add_((1.0 - beta2) * gg * gg)
+            p.sub_(np.float32(lr / bc1) * (m / (v.sqrt() * np.float32(1.0 / np.sqrt(bc2)) + eps)))
+            if zero_grad:
+                g.zero_()
+
+
 # ----------------------------------------------------------------------------- dispatch
 def call(name: str, *args) -> None:
     """Stand-in for ``emernerf_b200._lib.call``: same names, same positional arguments."""
