@@ -48,7 +48,16 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays in one CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-step", action="store_true", help="skip the pixel + lidar iteration timing")
     ap.add_argument("--profile-all", action="store_true", help="print the per-kernel time table of one step")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: emernerf_b200.optim.FusedAdam (one launch: Adam + gradient zeroing, flat buffers); "
+                         "torch: torch.optim.Adam(fused=True) as builders.py builds it")
+    ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"],
+                    help="multi-GPU gradient exchange (emernerf_b200.distributed): reduce-scatter + sharded Adam + "
+                         "all-gather, or all-reduce + replicated Adam")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rays per GPU; strong: --rays in total, split over the GPUs (BASELINE configs[3,4])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying "
                     "the captured CUDA graphs of the step")
     return ap.parse_args()
@@ -72,6 +81,29 @@ def pixel_losses(out, batch):
     if "forward_pred_backward_flow" in ex:
         loss = loss + 0.01 * 0.5 * ((ex["forward_flow"].detach() + ex["forward_pred_backward_flow"]) ** 2
                                     + (ex["backward_flow"].detach() + ex["backward_pred_forward_flow"]) ** 2).mean()
+    return loss
+
+
+def lidar_losses(out, batch, epsilon=2.0):
+    """The reference's lidar-pass losses (train_emernerf.py:772-820) as capturable tensor code: range loss
+    (loss/base.py:188-269: l2 of depths normalised by 80 m over rays with 0.01 < range < 80, coef 1), line-of-sight loss
+    (loss/base.py:430-464, coef 0.1, margin ``epsilon``) and the dynamic-density regulariser on lidar rays (Q13).
+    (The valid-ray mask multiplies instead of indexing, so shapes are static.)"""
+    gt = batch["lidar_ranges"].squeeze(-1)
+    valid = ((gt > 0.01) & (gt < 80.0)).float()
+    nd = lambda d: torch.clamp(d / 80.0, 0.0, 1.0)
+    loss = (((nd(out["depth"].squeeze(-1)) - nd(gt)) ** 2) * valid).sum() / valid.sum().clamp_min(1.0)
+    ex = out["extras"]
+    w, t = ex["weights"], ex["t_vals"].detach()
+    g = gt.unsqueeze(-1)
+    empty = (t < g - epsilon).float()
+    near = ((t > g - epsilon) & (t < g + epsilon)).float()
+    sig = epsilon / 3.0
+    dirac = (1.0 / (2.0 * torch.pi * sig * sig) ** 0.5) * torch.exp(-((t - g) ** 2) / (2.0 * sig * sig))
+    sight = ((w.square() * empty).sum(-1, keepdim=True).mean() + ((w - dirac).square() * near).sum(-1, keepdim=True).mean())
+    loss = loss + 0.1 * (sight * (gt > 0).float()).mean()
+    if "dynamic_density" in ex:
+        loss = loss + 0.01 * ex["dynamic_density"].mean()
     return loss
 
 
@@ -124,7 +156,13 @@ class Trainer:
         self.cfg = configs.make_cfg(args.variant, num_samples=args.samples)
         self.use_graph = not args.no_graph
         self.field, self.props, self.est, self.opt = configs.build_hot_path(self.cfg, device, table_std=0.3,
-                                                                            capturable=self.use_graph)
+                                                                            capturable=self.use_graph,
+                                                                            optimizer=args.optimizer)
+        self.dp = None
+        if args.optimizer == "fused":
+            from emernerf_b200.distributed import DataParallel
+
+            self.dp = DataParallel([self.opt, self.est.optimizer], mode=args.dp_mode)
         self.field.train(); self.est.train()
         [p.train() for p in self.props]
         self.req_fn = get_proposal_requires_grad_fn()
@@ -132,21 +170,29 @@ class Trainer:
         feats = args.variant == "flow_feat"
         nt = self.cfg.data.num_timesteps
         # 8 distinct batches per rank, cycled (device-resident and pinned-host copies)
-        self.host = [synthetic.pixel_batch(args.rays, nt, 3, seed=1000 * rank + i, features=feats, pin=True)
+        self.rays = args.rays if args.scaling == "weak" else args.rays // world     # rays THIS rank renders per step
+        self.host = [synthetic.pixel_batch(self.rays, nt, 3, seed=1000 * rank + i, features=feats, pin=True)
                      for i in range(8)]
         self.dev = [{k: v.to(device) for k, v in b.items()} for b in self.host]
         self.h2d_bytes = synthetic.bytes_of(self.host[0])
+        # the second half of a reference training iteration: a lidar-ray pass (train_emernerf.py:748-827)
+        self.lidar_dev = [{k: v.to(device) for k, v in synthetic.lidar_batch(self.rays, nt, seed=1000 * rank + i).items()}
+                          for i in range(4)]
         self.params = [p for p in self.field.parameters()]
         self.prop_params = [p for m in self.props for p in m.parameters()]
 
-    def allreduce(self, params):
-        if self.world == 1:
+    def sync_and_step(self, opt, params):
+        """Average the gradients over the ranks and take the optimizer step."""
+        if self.dp is not None:
+            self.dp.step(opt)                     # one flat collective per group (emernerf_b200/distributed.py)
             return
-        import torch.distributed as dist
+        if self.world > 1:
+            import torch.distributed as dist
 
-        grads = [p.grad for p in params if p.grad is not None]
-        for g in grads:                           # NCCL over NVLink; hash tables dominate (122 MB)
-            dist.all_reduce(g, op=dist.ReduceOp.AVG)
+            for p in params:                      # torch.optim.Adam arm: per-tensor all-reduce (round 1's recipe)
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        opt.step()
 
     # ---- CUDA graphs: the step is ~10^2 small launches; capture it once per schedule branch
     def build_graphs(self):
@@ -169,6 +215,51 @@ class Trainer:
                 self.static_loss[prg] = self._step_body(self.static, prg)
             self.graph_launches[prg] = _lib.LAUNCHES - n0      # library kernels inside this graph
             self.graphs[prg] = g
+
+    def lidar_step(self, i):
+        """The lidar half of a training iteration (device-resident rays): density-only render, range + line-of-sight
+        losses, backward, second Adam step; the proposal schedule advances once more (Q16)."""
+        prg = self.req_fn(self.step_idx)
+        self.step_idx += 1
+        if self.use_graph and not getattr(self, "_profiling", False):
+            if not hasattr(self, "lidar_graphs"):
+                self.build_lidar_graphs()
+            for k, v in self.lidar_static.items():
+                v.copy_(self.lidar_dev[i % 4][k], non_blocking=True)
+            self.lidar_graphs[prg].replay()
+            return self.lidar_loss[prg]
+        return self._lidar_body(self.lidar_dev[i % 4], prg)
+
+    def build_lidar_graphs(self):
+        self.lidar_static = {k: torch.empty_like(v) for k, v in self.lidar_dev[0].items()}
+        self.lidar_graphs, self.lidar_loss = {}, {}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for prg in (False, True, False):
+                self._lidar_body(self.lidar_static, prg)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for prg in (False, True):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.lidar_loss[prg] = self._lidar_body(self.lidar_static, prg)
+            self.lidar_graphs[prg] = g
+
+    def _lidar_body(self, batch, prg):
+        from emernerf_b200.radiance_fields.render_utils import render_rays
+
+        out = render_rays(self.field, self.est, self.props, batch, self.cfg, proposal_requires_grad=prg, prefix="lidar_")
+        if prg:
+            ploss = self.est.compute_loss(out["extras"]["trans"], 1024.0)
+            self.est.optimizer.zero_grad()
+            ploss.backward()
+            self.sync_and_step(self.est.optimizer, self.prop_params)
+        loss = lidar_losses(out, batch)
+        self.opt.zero_grad()
+        (loss * 1024.0).backward()
+        self.sync_and_step(self.opt, self.params)
+        return loss
 
     def step(self, i, from_host):
         prg = self.req_fn(self.step_idx)
@@ -196,13 +287,11 @@ class Trainer:
             ploss = self.est.compute_loss(out["extras"]["trans"], 1024.0)
             self.est.optimizer.zero_grad()
             ploss.backward()
-            self.allreduce(self.prop_params)
-            self.est.optimizer.step()
+            self.sync_and_step(self.est.optimizer, self.prop_params)
         loss = pixel_losses(out, batch)
         self.opt.zero_grad()
         (loss * 1024.0).backward()                # GradScaler(2**10).scale(loss), never unscaled (Q17)
-        self.allreduce(self.params)
-        self.opt.step()
+        self.sync_and_step(self.opt, self.params)
         return loss
 
 
@@ -291,9 +380,34 @@ def run_ours(args):
         for i in range(2):
             tr.step(i, True)
         ms_e2e = timed(tr, args.steps, True, sync)
-        e2e = {"value": args.rays * world * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+        e2e = {"value": tr.rays * world * args.steps / (ms_e2e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": tr.h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}
+
+    # a whole reference training iteration: pixel pass + lidar pass, two (three) optimizer steps
+    full = None
+    if not args.no_full_step:
+        for i in range(3):
+            tr.step(i, False); tr.lidar_step(i)
+        sync()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        n_full = max(8, args.steps // 4)
+        for i in range(n_full):
+            tr.step(i, False)
+            tr.lidar_step(i)
+        f1.record()
+        sync()
+        ms_full = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms_full], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_full = t.item()
+        full = {"ms_per_iteration": ms_full / n_full, "iterations": n_full,
+                "pixel_rays_per_s": tr.rays * world * n_full / (ms_full / 1e3),
+                "rays_per_s_pixel_plus_lidar": 2 * tr.rays * world * n_full / (ms_full / 1e3),
+                "what": f"one reference training iteration (train_emernerf.py:612-827): {tr.rays} pixel rays (fwd + bwd + Adam)"
+                        f" + {tr.rays} lidar rays per GPU (density-only render, range + line-of-sight losses, bwd, second Adam)"}
 
     # per-kernel device times: CUDA events around every library launch over 3 eager steps, same
     # process / inputs / clocks, right after the timed region (a replayed graph cannot be event-timed
@@ -394,12 +508,17 @@ def run_ours(args):
     dom_ms = per_launch[dom]
     by_name = {k: v[1] for k, v in table.items()}
     line = {
-        "metric": METRIC, "value": args.rays * world * args.steps / (ms / 1e3), "unit": UNIT,
+        "metric": METRIC, "value": tr.rays * world * args.steps / (ms / 1e3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic Waymo-shape rays (3 cams, 640x960, 200 timesteps), random-init MLPs, N(0,0.3) tables",
         "config": dict(workload_config(args, world),
-                       l2="no explicit flush: each step streams > 1 GB of tables+activations through the 126 MB L2"),
+                       l2="no explicit flush: each step streams > 1 GB of tables+activations through the 126 MB L2",
+                       optimizer=args.optimizer,
+                       gradient_exchange=("none (1 GPU)" if world == 1 else
+                                          (f"{args.dp_mode}: one flat NCCL collective per optimizer group, "
+                                           f"{tr.dp.bytes_per_step(tr.opt) / 1e6:.0f} MB sent per rank per step"
+                                           if tr.dp is not None else "per-tensor all-reduce"))),
         "gpu_launches": launches,
         "dominant_kernel": {"name": f"{dom[0]}[{dom[1]}]", "share_of_library_kernel_time": by_name[dom] / tot_ms,
                             "avg_launch_ms": dom_ms},
@@ -409,6 +528,8 @@ def run_ours(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if full is not None:
+        line["full_step"] = full
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args, steps=2, warmup=1)
         line.update(parity_vs_oracle(tr, args))         # second half of BASELINE.json's metric: PSNR vs reference
@@ -424,10 +545,11 @@ def run_ours(args):
 # ----------------------------------------------------------------------------- the CPU arm
 def workload_config(args, world):
     """The ``config`` both arms report: BASELINE.json's configuration the metric is quoted on."""
+    per_gpu = args.rays if getattr(args, "scaling", "weak") == "weak" else args.rays // world
     return {"workload": f"BASELINE configs[{['static', 'dynamic', 'flow', 'flow_feat'].index(args.variant) + 1}]: "
-                        f"default_config {args.variant} field, {args.rays} rays x {args.samples} samples "
+                        f"default_config {args.variant} field, {per_gpu} rays x {args.samples} samples "
                         f"per GPU, proposal samples [128, 64], fwd+bwd+Adam, proposal update every ~6th step",
-            "rays_per_gpu": args.rays, "samples": args.samples, "parallelism": f"ray-sharded dp{world}"}
+            "rays_per_gpu": per_gpu, "samples": args.samples, "parallelism": f"ray-sharded dp{world}"}
 
 
 def cpu_baseline(args, steps, warmup):

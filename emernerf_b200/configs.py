@@ -55,10 +55,12 @@ def make_cfg(variant: str = "static", num_timesteps: int = 200, num_cams: int = 
               variant=variant)
 
 
-def build_hot_path(cfg: NS, device="cuda", table_std: float = 0.0, seed: int = 0, capturable: bool = False):
+def build_hot_path(cfg: NS, device="cuda", table_std: float = 0.0, seed: int = 0, capturable: bool = False,
+                   optimizer: str = "torch"):
     """(field, proposal_networks, estimator, optimizer) as builders.py builds them.  ``table_std > 0``
     replaces tcnn's degenerate U(-1e-4, 1e-4) table init by N(0, table_std) ("trained-like" state for
-    bandwidth measurements)."""
+    bandwidth measurements).  ``optimizer``: "torch" = torch.optim.Adam exactly as builders.py:50-61
+    constructs it, "fused" = emernerf_b200.optim.FusedAdam (same arithmetic, one launch per step, flat buffers)."""
     from .radiance_fields import build_density_field, build_radiance_field_from_cfg
     from .third_party.nerfacc_prop_net import PropNetEstimator
 
@@ -87,6 +89,14 @@ def build_hot_path(cfg: NS, device="cuda", table_std: float = 0.0, seed: int = 0
     field = field.to(device)
     props = [p.to(device) for p in props]
     adam = dict(lr=cfg.optim.lr, eps=1e-15, weight_decay=cfg.optim.weight_decay, betas=(0.9, 0.99))
+    if optimizer == "fused":
+        from .optim import FusedAdam
+
+        prop_opt = FusedAdam(itertools.chain(*[p.parameters() for p in props]), flatten_params=True, **adam)
+        est = PropNetEstimator(prop_opt, None,
+                               enable_anti_aliasing_loss=cfg.nerf.propnet.enable_anti_aliasing_level_loss,
+                               anti_aliasing_pulse_width=cfg.nerf.propnet.anti_aliasing_pulse_width).to(device)
+        return field, props, est, FusedAdam(field.parameters(), flatten_params=True, **adam)
     if capturable:                      # CUDA-graph capture of the optimizer step
         adam["capturable"] = True
     if str(device).startswith("cuda"):  # one fused kernel per step instead of the foreach chain (same maths)

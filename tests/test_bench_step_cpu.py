@@ -53,6 +53,7 @@ def test_training_step_of_both_arms_is_the_same_computation(monkeypatch, variant
     tr = bench.Trainer.__new__(bench.Trainer)
     tr.args = types.SimpleNamespace(variant=variant, rays=n_rays, samples=samples)
     tr.rank, tr.world, tr.device, tr.cfg = 0, 1, "cpu", cfg
+    tr.dp = None                      # torch.optim.Adam arm: the gradients stay inspectable after the step
     tr.field, tr.props, tr.est, tr.opt = field, props, est, opt
     tr.params = list(field.parameters())
     tr.prop_params = [p for m in props for p in m.parameters()]
@@ -86,3 +87,46 @@ def test_training_step_of_both_arms_is_the_same_computation(monkeypatch, variant
     del cabi_emulator.CALLS[:]
     tr._step_body(batch, False)
     assert "emer_prop_level" in cabi_emulator.CALLS
+
+
+def test_lidar_half_of_the_iteration_runs_and_matches_the_reference_losses(monkeypatch):
+    """bench.py's lidar pass (density-only render, range + line-of-sight losses, backward, second Adam step) on CPU
+    through the emulator; its loss restated with the reference's own formulas (boolean indexing, loss/base.py:188-269,
+    430-464) gives the same number."""
+    from emernerf_b200 import configs, synthetic
+
+    bench = _bench()
+    cabi_emulator.install(monkeypatch)
+    cfg = configs.make_cfg("dynamic", num_samples=64)
+    field, props, est, opt = configs.build_hot_path(cfg, "cpu", table_std=0.3)
+    tr = bench.Trainer.__new__(bench.Trainer)
+    tr.rank, tr.world, tr.device, tr.cfg, tr.dp = 0, 1, "cpu", cfg, None
+    tr.field, tr.props, tr.est, tr.opt = field, props, est, opt
+    tr.params = list(field.parameters())
+    tr.prop_params = [p for m in props for p in m.parameters()]
+    field.train(); est.train()
+    [p.train() for p in props]
+    lb = synthetic.lidar_batch(24, cfg.data.num_timesteps, seed=3)
+    before = field.xyz_encoder.tcnn_encoding.params.detach().clone()
+    torch.manual_seed(7)
+    loss = tr._lidar_body(lb, False)
+    assert torch.isfinite(loss) and not torch.equal(field.xyz_encoder.tcnn_encoding.params.detach(), before)
+
+    from emernerf_b200.radiance_fields.render_utils import render_rays
+    torch.manual_seed(7)
+    field.eval(); est.eval()
+    with torch.no_grad():
+        out = render_rays(field, est, props, lb, cfg, prefix="lidar_")
+    gt = lb["lidar_ranges"].squeeze()
+    pred = out["depth"].squeeze()
+    valid = (gt > 0.01) & (gt < 80)
+    want = torch.nn.functional.mse_loss(torch.clamp(pred[valid] / 80, 0, 1), torch.clamp(gt[valid] / 80, 0, 1))
+    w, t = out["extras"]["weights"], out["extras"]["t_vals"]
+    g = gt.unsqueeze(-1)
+    eps = 2.0
+    dirac = (1 / (2 * torch.pi * (eps / 3) ** 2) ** 0.5) * torch.exp(-((t - g) ** 2) / (2 * (eps / 3) ** 2))
+    sight = ((w.square() * (t < g - eps)).sum(-1, keepdim=True).mean()
+             + ((w - dirac).square() * ((t > g - eps) & (t < g + eps))).sum(-1, keepdim=True).mean()) * (gt > 0)
+    want = want + 0.1 * sight.mean() + 0.01 * out["extras"]["dynamic_density"].mean()
+    got = bench.lidar_losses(out, lb)
+    assert abs(got.item() - want.item()) <= 1e-6 * max(1.0, abs(want.item()))

@@ -563,3 +563,34 @@ def test_field_chain_inference_writes_no_saves():
     assert g0 is None
     s1, c1, _, _ = _ops.field_chain(enc.clone().requires_grad_(True), rb, S, ws[:4], ws[4:])
     assert torch.equal(s0, s1) and torch.equal(c0, c1)
+
+
+# ----------------------------------------------------------------------------- optimizer
+def test_fused_adam_matches_torch_adam_on_device():
+    """emer_adam_step (csrc/optim.cu) through emernerf_b200.optim.FusedAdam: same gradients in, torch.optim.Adam's
+    parameters out (<= 1e-6 after 5 steps: the two differ only in FMA contraction and the fp64 bias corrections),
+    gradients zeroed by the step, untouched parameters skipped, ragged block sizes."""
+    from emernerf_b200 import _ops
+    from emernerf_b200.optim import FusedAdam
+
+    _ops.clear_grad_sinks()
+    adam = dict(lr=0.01, eps=1e-15, weight_decay=1e-5, betas=(0.9, 0.99))
+    torch.manual_seed(2)
+    shapes = ((1 << 21,), (64, 40), (64,), (3, 64), (1000003,), (7,))
+    pa = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    idle = torch.nn.Parameter(torch.randn(100, device=DEV))
+    idle0 = idle.detach().clone()
+    a, b = torch.optim.Adam(pa, **adam), FusedAdam(pb + [idle], **adam)
+    for step in range(5):
+        for x, y in zip(pa, pb):
+            gr = torch.randn_like(x) * (10.0 ** (step - 2))
+            x.grad = gr.clone()
+            y.grad.add_(gr)
+            b._mark(y)
+        a.step(); b.step()
+        assert all(float(g.abs().max()) == 0.0 for g in b.flat_grads())
+    for x, y in zip(pa, pb):
+        assert rel_err(y, x) < 1e-6, rel_err(y, x)
+    assert torch.equal(idle.detach(), idle0)              # never touched: no update, no weight decay
+    _ops.clear_grad_sinks()
