@@ -98,6 +98,51 @@ def _grad_sink(t: Optional[Tensor]):
     return sink, (lambda: on_touch(p))
 
 
+# ----------------------------------------------------------------------------- weight gradients on a side stream
+# EMER_WGRAD_STREAM=1: the fused chain's weight-gradient kernels run on a side stream, forked where the dZ buffers are
+# complete.  The main stream goes on to the hash-grid scatter and -- multi-GPU -- to the reduce-scatter of the table
+# gradients, which no weight gradient feeds; the optimizer (or the reduction of the MLP gradients) joins the side stream
+# first (:func:`join_side_streams`).  Captured into the step's CUDA graph this becomes two parallel branches.
+WGRAD_STREAM = os.environ.get("EMER_WGRAD_STREAM", "0") == "1"
+_SIDE: Dict[int, "torch.cuda.Stream"] = {}
+_PENDING: Dict[int, bool] = {}
+_AFTER_JOIN: list = []          # small updates of buffers the main stream also writes: run there, after the join
+
+
+class _on_side_stream:
+    """Context: launch on the device's side stream after everything enqueued so far on the current stream; tensors
+    listed are marked as used there (the caching allocator must not hand their memory out early)."""
+
+    def __init__(self, device, *tensors):
+        self.dev, self.tensors = device, [t for t in tensors if t is not None]
+
+    def __enter__(self):
+        idx = self.dev.index
+        if idx not in _SIDE:
+            _SIDE[idx] = torch.cuda.Stream(device=self.dev)
+        side, main = _SIDE[idx], torch.cuda.current_stream(self.dev)
+        side.wait_stream(main)
+        for t in self.tensors:
+            t.record_stream(side)
+        _PENDING[idx] = True
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return side
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
+def join_side_streams() -> None:
+    """The current stream waits for weight gradients still running on a side stream (no-op when there are none)."""
+    for idx, pending in list(_PENDING.items()):
+        if pending:
+            torch.cuda.current_stream(idx).wait_stream(_SIDE[idx])
+            _PENDING[idx] = False
+    while _AFTER_JOIN:
+        _AFTER_JOIN.pop(0)()
+
+
 def _f32c(t: Tensor) -> Tensor:
     if t.dtype != torch.float32:
         t = t.to(torch.float32)
@@ -673,7 +718,8 @@ class _FieldChain(torch.autograd.Function):
         w1hg = torch.cat([w1[:, :64], w1[:, 64 + n_ray_cols:]], dim=1)            # [64, 128] = [hidden | geo] columns
         w0g = w0[:, n_ray_cols:].contiguous()
         D1 = torch.empty((n, 128), **f32)          # [dZ0 | dF] side by side (row stride 128)
-        dw0 = dw1 = dw2 = db2 = d_rb = d_enc = None
+        dw2 = db2 = dw1hg = dw0g = dz2 = dz1 = d_rb = d_enc = None
+        fused_data = False
         c = lambda g, w: None if g is None else _f32c(g.reshape(n, w))
         d_geo, d_sem = c(d_geo, 64), c(d_sem, 64)
         if CHAIN_BWD == "fused" and samples % 32 == 0 and _tc_rows_ok(n):
@@ -690,10 +736,7 @@ class _FieldChain(torch.autograd.Function):
                       _ptr(hg), _ptr(h1), _ptr(wb0), k_enc, _ptr(wb1), n_feat, _ptr(w0g), 64, _ptr(w1hg), _ptr(w1hg[:, 64:]),
                       128, _ptr(w2), _ptr(dz2), _ptr(dz1), _ptr(D1), _ptr(dzb), _ptr(d_enc), k_enc, _ptr(d_rb), samples, n,
                       _stream())
-            if d_rgb is not None:
-                dw2, db2 = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n, sk["w2"], sk["b2"])
-                dw1hg, _ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)
-                dw0g, _ = _layer_bwd_weight(hg[:, 64:], 128, D1[:, :64], 128, w0g, False, n)
+            fused_data = True
         else:
             # ---- layer by layer on the same buffers (ragged rays, tiny batches, EMER_CHAIN_BWD=layers)
             if d_rgb is not None:
@@ -726,28 +769,11 @@ class _FieldChain(torch.autograd.Function):
                 # trunc_exp backward (nerf_utils.py:72-75): g * exp(clamp(x, max=15)), x = feats[:, 0] - 1 = log(sigma)
                 dgeo[:, 0] += _f32c(d_sigma).reshape(n) * torch.clamp(sigma, max=3269017.25)
             dzb = None
-        if d_rgb is not None:
-            # the head's geo / hidden column blocks; its per-ray columns get their gradient through ray_bias
-            if sk["w0"] is not None:
-                sk["w0"][0][:, n_ray_cols:] += dw0g
-                sk["w0"][1]()
-            else:
-                dw0 = torch.zeros_like(w0)
-                dw0[:, n_ray_cols:] = dw0g
-            if sk["w1"] is not None:
-                sk["w1"][0][:, :64] += dw1hg[:, :64]
-                sk["w1"][0][:, 64 + n_ray_cols:] += dw1hg[:, 64:]
-                sk["w1"][1]()
-            else:
-                dw1 = torch.zeros_like(w1)
-                dw1[:, :64] = dw1hg[:, :64]
-                dw1[:, 64 + n_ray_cols:] = dw1hg[:, 64:]
         if n_feat == 128:
             dfe = torch.cat([D1[:, 64:], torch.zeros((n, 64), **f32) if d_sem is None else d_sem], dim=1)
             ldf = 128
         else:
             dfe, ldf = D1[:, 64:], 128
-        dwb1, dbb1 = _layer_bwd_weight(hb, 64, dfe, ldf, wb1, True, n, sk["wb1"], sk["bb1"])
         if dzb is None:
             dzb = torch.empty((n, 64), **f32)
             _layer_bwd_data(dfe, ldf, wb1, dzb, 64, n, hb, 64, 64)
@@ -755,7 +781,49 @@ class _FieldChain(torch.autograd.Function):
                 d_enc = torch.empty((n, _pad4(k_enc)), **f32)
                 _layer_bwd_data(dzb, 64, wb0, d_enc, d_enc.shape[1], n, None, 0, 0)
                 d_enc = d_enc[:, :k_enc]
-        dwb0, dbb0 = _layer_bwd_weight(enc2, ld_enc, dzb, 64, wb0, True, n, sk["wb0"], sk["bb0"])
+
+        res = {}
+
+        def weight_gradients(deferred=None):
+            """X^T dZ over all rows for the five layers (+ the column-block bookkeeping of the head's weights; on the
+            side stream those few adds are deferred to the join: autograd adds the per-ray columns' gradient to the same
+            tensors on the main stream)."""
+            dw0 = dw1 = dw2_ = db2_ = None
+            add = (lambda dst, src: dst.add_(src)) if deferred is None else (lambda dst, src: deferred.append(lambda: dst.add_(src)))
+            if d_rgb is not None:
+                if fused_data:
+                    dw2_, db2_ = _layer_bwd_weight(h1, 64, dz2, 3, w2, True, n, sk["w2"], sk["b2"])
+                    dw1hg_ = _layer_bwd_weight(hg, 128, dz1, 64, w1hg, False, n)[0]
+                    dw0g_ = _layer_bwd_weight(hg[:, 64:], 128, D1[:, :64], 128, w0g, False, n)[0]
+                else:
+                    dw2_, db2_, dw1hg_, dw0g_ = dw2, db2, dw1hg, dw0g
+                # the head's geo / hidden column blocks; its per-ray columns get their gradient through ray_bias
+                if sk["w0"] is not None:
+                    add(sk["w0"][0][:, n_ray_cols:], dw0g_)
+                    sk["w0"][1]()
+                else:
+                    dw0 = torch.zeros_like(w0)
+                    dw0[:, n_ray_cols:] = dw0g_
+                if sk["w1"] is not None:
+                    add(sk["w1"][0][:, :64], dw1hg_[:, :64])
+                    add(sk["w1"][0][:, 64 + n_ray_cols:], dw1hg_[:, 64:])
+                    sk["w1"][1]()
+                else:
+                    dw1 = torch.zeros_like(w1)
+                    dw1[:, :64] = dw1hg_[:, :64]
+                    dw1[:, 64 + n_ray_cols:] = dw1hg_[:, 64:]
+            dwb1, dbb1 = _layer_bwd_weight(hb, 64, dfe, ldf, wb1, True, n, sk["wb1"], sk["bb1"])
+            dwb0, dbb0 = _layer_bwd_weight(enc2, ld_enc, dzb, 64, wb0, True, n, sk["wb0"], sk["bb0"])
+            res["g"] = (dwb0, dbb0, dwb1, dbb1, dw0, dw1, dw2_, db2_)
+
+        if WGRAD_STREAM and fused_data and all(v is not None for v in sk.values()) and enc2.is_cuda:
+            # every weight gradient lands in the optimizer's buffers: nothing autograd waits for, so the kernels may run
+            # beside the hash-grid scatter / the table's reduce-scatter (joined by FusedAdam.step / DataParallel.reduce)
+            with _on_side_stream(dev, enc2, hb, hg, h1, dz2, dz1, D1, dzb, dfe, w1hg, w0g):
+                weight_gradients(_AFTER_JOIN)
+        else:
+            weight_gradients()
+        dwb0, dbb0, dwb1, dbb1, dw0, dw1, dw2, db2 = res["g"]
         if d_enc is not None:
             d_enc = d_enc.reshape(enc_shape)
         return d_enc, d_rb, None, None, dwb0, dbb0, dwb1, dbb1, dw0, dw1, dw2, db2

@@ -92,11 +92,19 @@ def build_hot_path(cfg: NS, device="cuda", table_std: float = 0.0, seed: int = 0
     if optimizer == "fused":
         from .optim import FusedAdam
 
-        prop_opt = FusedAdam(itertools.chain(*[p.parameters() for p in props]), flatten_params=True, **adam)
+        def groups(mods):
+            """Two flat buckets per optimizer: the hash tables (the big gradients, complete as soon as the grid
+            scatter has run) first, everything else (MLPs, embedding, PE map) last -- the order DataParallel reduces in."""
+            named = [(k, v) for m in mods for k, v in m.named_parameters()]
+            tables = [v for k, v in named if k.endswith("tcnn_encoding.params")]
+            rest = [v for k, v in named if not k.endswith("tcnn_encoding.params")]
+            return [{"params": tables}, {"params": rest}]
+
+        prop_opt = FusedAdam(groups(props), flatten_params=True, **adam)
         est = PropNetEstimator(prop_opt, None,
                                enable_anti_aliasing_loss=cfg.nerf.propnet.enable_anti_aliasing_level_loss,
                                anti_aliasing_pulse_width=cfg.nerf.propnet.anti_aliasing_pulse_width).to(device)
-        return field, props, est, FusedAdam(field.parameters(), flatten_params=True, **adam)
+        return field, props, est, FusedAdam(groups([field]), flatten_params=True, **adam)
     if capturable:                      # CUDA-graph capture of the optimizer step
         adam["capturable"] = True
     if str(device).startswith("cuda"):  # one fused kernel per step instead of the foreach chain (same maths)

@@ -24,6 +24,7 @@ from typing import List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from . import _ops
 from .optim import ALIGN, FusedAdam
 
 
@@ -61,7 +62,11 @@ class DataParallel:
         """Average ``opt``'s flat gradients over the ranks (all of it, or -- sharded -- this rank's slice in place)."""
         if not self.on:
             return
-        for g in opt._groups:
+        for gi, g in enumerate(opt._groups):
+            if gi == len(opt._groups) - 1:
+                # the LAST group holds the MLP weights, whose gradients may still be running on a side stream
+                # (EMER_WGRAD_STREAM=1): the table groups in front of it are reduced meanwhile
+                _ops.join_side_streams()
             flat = g.grad
             if self.mode == "allreduce":
                 if self.native:

@@ -146,6 +146,7 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        _ops.join_side_streams()                 # weight gradients that ran beside the rest of the backward pass
         for group, g in zip(self.param_groups, self._groups):
             active = tuple(i for i, p in enumerate(g.params) if id(p) in self._touched)
             if not active:
