@@ -213,6 +213,16 @@ int emer_accumulate_fwd(const float* w, const float* v, float* out, int64_t n_ra
 int emer_accumulate_bwd(const float* w, const float* v, const float* g, float* dw, float* dv,
                         int64_t n_rays, int n_samples, int c, void* stream);
 
+/* ---- ray generation (replaces datasets/base/pixel_source.py:39-76 get_rays and the per-ray gathers / coordinate
+ *      assembly of get_train_rays, :699-719) ------------------------------------------------------------------ */
+/* Per ray i: m = img_idx[i] (or i when per_ray_mats, or 0), c2w[m] (4x4 row-major), intrinsics[m] (3x3):
+ *   origins[i] = c2w[:3,3];  viewdirs[i] = R cam / (|R cam| + 1e-8), cam = ((x-cx+.5)/fx, (y-cy+.5)/fy, 1);
+ *   norms[i] = |R cam|;  pixel_coords[i] = (y / height, x / width);  out_times[i] = timestamps[m].
+ * img_idx (int64), norms, pixel_coords, out_times / timestamps may be NULL. */
+int emer_gen_rays(const int64_t* img_idx, const float* x, const float* y, const float* c2w, const float* intrinsics,
+                  int per_ray_mats, const float* timestamps, int height, int width, float* origins, float* viewdirs,
+                  float* norms, float* pixel_coords, float* out_times, int64_t n, void* stream);
+
 /* ---- optimizer (replaces torch.optim.Adam's step + optimizer.zero_grad() + tiny-cuda-nn's gradient memset,
  *      builders.py:50-61,114-120; train_emernerf.py:742-745,823-826) --------------------------------------------- */
 /* One parameter block: n fp32 values of a parameter, its gradient and Adam moments (16-byte aligned, device). */

@@ -497,6 +497,34 @@ def emer_field_bwd(d_rgb, rgb, d_sigma, sigma, d_geo, d_sem, hb, hg, h1, wb0, k_
             acc[:, 64:].index_add_(0, ray, z1)
 
 
+# ----------------------------------------------------------------------------- ray generation
+def emer_gen_rays(img_idx, x, y, c2w, intrinsics, per_ray_mats, timestamps, height, width, origins, viewdirs, norms,
+                  pixel_coords, out_times, n, stream):
+    if n == 0:
+        return
+    _require(not _addr(pixel_coords) or (height > 0 and width > 0), "emer_gen_rays: pixel coordinates need the image size")
+    xs, ys = _vec(x, n), _vec(y, n)
+    if _addr(img_idx):
+        idx = _vec(img_idx, n, ctype=ctypes.c_int64, dtype=np.int64)
+        n_m = int(idx.max()) + 1
+    else:
+        idx = torch.arange(n) if per_ray_mats else torch.zeros(n, dtype=torch.int64)
+        n_m = n if per_ray_mats else 1
+    C = _view(c2w, n_m, 16)[idx].view(n, 4, 4)
+    K = _view(intrinsics, n_m, 9)[idx].view(n, 3, 3)
+    cam = torch.stack([(xs - K[:, 0, 2] + 0.5) / K[:, 0, 0], (ys - K[:, 1, 2] + 0.5) / K[:, 1, 1], torch.ones(n)], -1)
+    d = (cam[:, None, :] * C[:, :3, :3]).sum(-1)
+    nrm = torch.linalg.norm(d, dim=-1, keepdims=True)
+    _view(origins, n, 3).copy_(C[:, :3, 3])
+    _view(viewdirs, n, 3).copy_(d / (nrm + 1e-8))
+    if _addr(norms):
+        _view(norms, n, 1).copy_(nrm)
+    if _addr(pixel_coords):
+        _view(pixel_coords, n, 2).copy_(torch.stack([ys / height, xs / width], -1))
+    if _addr(out_times) and _addr(timestamps):
+        _vec(out_times, n).copy_(_vec(timestamps, n_m)[idx])
+
+
 # ----------------------------------------------------------------------------- optimizer
 def emer_adam_step(blocks, prefix, n_blocks, total, hyper, beta1, beta2, eps, weight_decay, zero_grad, stream):
     if n_blocks == 0 or total == 0:

@@ -594,3 +594,40 @@ def test_fused_adam_matches_torch_adam_on_device():
         assert rel_err(y, x) < 1e-6, rel_err(y, x)
     assert torch.equal(idle.detach(), idle0)              # never touched: no update, no weight decay
     _ops.clear_grad_sinks()
+
+
+# ----------------------------------------------------------------------------- ray generation
+def _get_rays_reference(x, y, c2w, intrinsic):
+    """datasets/base/pixel_source.py:39-76, restated."""
+    cam = torch.nn.functional.pad(torch.stack([(x - intrinsic[:, 0, 2] + 0.5) / intrinsic[:, 0, 0],
+                                               (y - intrinsic[:, 1, 2] + 0.5) / intrinsic[:, 1, 1]], dim=-1), (0, 1), value=1.0)
+    directions = (cam[:, None, :] * c2w[:, :3, :3]).sum(dim=-1)
+    origins = torch.broadcast_to(c2w[:, :3, -1], directions.shape)
+    norm = torch.linalg.norm(directions, dim=-1, keepdims=True)
+    return origins, directions / (norm + 1e-8), norm
+
+
+def test_gen_rays_matches_the_reference_formula():
+    from emernerf_b200 import raygen, synthetic
+
+    g = torch.Generator().manual_seed(5)
+    M, R, Hh, Ww = 600, 8192 + 13, 640, 960
+    c2w = torch.eye(4).repeat(M, 1, 1)
+    yaw = torch.rand(M, generator=g) * 6.28
+    c2w[:, 0, 0], c2w[:, 0, 1], c2w[:, 1, 0], c2w[:, 1, 1] = torch.cos(yaw), -torch.sin(yaw), torch.sin(yaw), torch.cos(yaw)
+    c2w[:, :3, 3] = torch.randn(M, 3, generator=g) * 30
+    K = torch.tensor([[1030.0, 0, 480.0], [0, 1030.0, 320.0], [0, 0, 1.0]]).repeat(M, 1, 1) * (1 + 0.01 * torch.rand(M, 1, 1, generator=g))
+    ts = torch.linspace(0, 1, M)
+    idx = torch.randint(0, M, (R,), generator=g)
+    y, x = torch.randint(0, Hh, (R,), generator=g), torch.randint(0, Ww, (R,), generator=g)
+    out = raygen.train_rays(idx.to(DEV), y.to(DEV), x.to(DEV), c2w.to(DEV), K.to(DEV), Hh, Ww, ts.to(DEV))
+    o, d, n = _get_rays_reference(x.float(), y.float(), c2w[idx], K[idx])
+    assert torch.equal(out["origins"].cpu(), o)
+    assert rel_err(out["viewdirs"], d) < 1e-6 and rel_err(out["direction_norms"], n) < 1e-6
+    assert torch.equal(out["pixel_coords"].cpu(), torch.stack([y / Hh, x / Ww], -1))
+    assert torch.equal(out["normed_timestamps"].cpu(), ts[idx]) and torch.equal(out["img_idx"].cpu(), idx)
+    # the reference's own call shape: per-ray gathered matrices
+    o2, d2, n2 = raygen.get_rays(x.float().to(DEV), y.float().to(DEV), c2w[idx].to(DEV), K[idx].to(DEV))
+    assert torch.equal(o2, out["origins"]) and torch.equal(d2, out["viewdirs"]) and torch.equal(n2, out["direction_norms"])
+    # unit directions
+    assert float((out["viewdirs"].norm(dim=-1) - 1).abs().max()) < 1e-6

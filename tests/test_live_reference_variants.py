@@ -71,3 +71,30 @@ def test_train_script_import_block_runs_after_install_dropin(tmp_path):
         assert "emernerf_b200" not in res[k], (k, res[k])
     assert "nerfacc" not in res["stubbed"] and "tinycudann" not in res["stubbed"]
     assert res["los_err"] < 1e-6
+
+
+@pytest.mark.reference
+def test_raygen_module_matches_the_reference_get_rays(monkeypatch):
+    """emernerf_b200.raygen.get_rays (host side through the emulator) against the reference's own function, executed
+    from its source file (datasets/base/pixel_source.py:39-76; the module's other imports are not needed)."""
+    import types
+
+    import torch
+
+    import cabi_emulator
+    from emernerf_b200 import raygen
+
+    cabi_emulator.install(monkeypatch)
+    src = open("/root/reference/datasets/base/pixel_source.py").read()
+    body = src[src.index("def get_rays("):src.index("class ScenePixelSource")]
+    ns = {}
+    exec("import torch\nfrom torch import Tensor\nfrom typing import Tuple\n" + body, ns)
+    g = torch.Generator().manual_seed(0)
+    R = 777
+    x, y = torch.randint(0, 960, (R,), generator=g).float(), torch.randint(0, 640, (R,), generator=g).float()
+    c2w = torch.eye(4).repeat(R, 1, 1) + torch.randn(R, 4, 4, generator=g) * 0.3
+    K = torch.tensor([[1030.0, 0, 480], [0, 1030, 320], [0, 0, 1]]).repeat(R, 1, 1)
+    for a, b in zip(raygen.get_rays(x, y, c2w, K), ns["get_rays"](x, y, c2w, K)):
+        assert torch.equal(a, b)
+    for a, b in zip(raygen.get_rays(x, y, c2w[0], K[0]), ns["get_rays"](x, y, c2w[0], K[0])):
+        assert torch.equal(a, b)
