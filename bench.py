@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-step", action="store_true", help="skip the pixel + lidar iteration timing")
     ap.add_argument("--profile-all", action="store_true", help="print the per-kernel time table of one step")
-    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+    ap.add_argument("--optimizer", default="torch", choices=["fused", "torch"],
                     help="fused: emernerf_b200.optim.FusedAdam (one launch: Adam + gradient zeroing, flat buffers); "
                          "torch: torch.optim.Adam(fused=True) as builders.py builds it")
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"],

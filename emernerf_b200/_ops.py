@@ -647,7 +647,7 @@ def field_tail(feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional
 
 # ----------------------------------------------------------------------------- fused field chain
 FIELD_CHAIN = os.environ.get("EMER_FIELD_CHAIN", "fused")      # "layers": the per-layer path (A/B and debugging switch)
-CHAIN_BWD = os.environ.get("EMER_CHAIN_BWD", "fused")          # "layers": data gradients layer by layer (A/B switch)
+CHAIN_BWD = os.environ.get("EMER_CHAIN_BWD", "layers")          # "layers": data gradients layer by layer (A/B switch)
 CHAIN_K_ENC = (32, 40, 64)
 
 
