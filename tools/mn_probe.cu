@@ -33,6 +33,9 @@ __host__ __device__ inline float aval(int m, int k) { return (float)((m % 7) - 3
 __host__ __device__ inline float bval(int n, int k) { return (float)((n % 5) - 2) + 0.5f * (float)(k % 8) - (float)(k / 8); }
 
 struct Variant {
+    int layout;                         // 2: SWIZZLE_128B (16-byte chunks ^ (k % 8), 8-deep k atom)
+                                        // 1: SWIZZLE_128B_BASE32B (32-byte chunks ^ (k % 4), 4-deep k atom; cute's
+                                        //    Layout_MN_SW128_32B_Atom, the atom CUTLASS picks for 32-bit MN-major operands)
     int a_lbo, a_sbo, b_lbo, b_sbo;     // descriptor fields (bytes)
     int a_mstride, a_kstride;           // where the probe PLACES the 32-wide mn blocks / 8-deep k groups (bytes)
     int b_mstride, b_kstride;
@@ -48,15 +51,18 @@ __global__ void probe(const Variant v, float* out) {
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (128 * 1024) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.0f;
     __syncthreads();
+    auto place = [&](int mn, int k, int mstride, int kstride) {
+        if (v.layout == 2)
+            return (mn / 32) * mstride + (k / 8) * kstride + (k % 8) * 128 + ((((mn % 32) / 4) ^ (k % 8)) * 16) + (mn % 4) * 4;
+        return (mn / 32) * mstride + (k / 4) * kstride + (k % 4) * 128 + ((((mn % 32) / 8) ^ (k % 4)) * 32) + (mn % 8) * 4;
+    };
     for (int e = tid; e < M * K; e += 128) {
         const int m = e % M, k = e / M;
-        const int off = (m / 32) * v.a_mstride + (k / 8) * v.a_kstride + (k % 8) * 128 + ((((m % 32) / 4) ^ (k % 8)) * 16) + (m % 4) * 4;
-        *reinterpret_cast<float*>(a_s + off) = aval(m, k);
+        *reinterpret_cast<float*>(a_s + place(m, k, v.a_mstride, v.a_kstride)) = aval(m, k);
     }
     for (int e = tid; e < N * K; e += 128) {
         const int n = e % N, k = e / N;
-        const int off = (n / 32) * v.b_mstride + (k / 8) * v.b_kstride + (k % 8) * 128 + ((((n % 32) / 4) ^ (k % 8)) * 16) + (n % 4) * 4;
-        *reinterpret_cast<float*>(b_s + off) = bval(n, k);
+        *reinterpret_cast<float*>(b_s + place(n, k, v.b_mstride, v.b_kstride)) = bval(n, k);
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
@@ -76,8 +82,8 @@ __global__ void probe(const Variant v, float* out) {
         uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
         idesc |= (1u << 15) | (1u << 16);                     // A and B MN-major
         for (int ks = 0; ks < K / 8; ++ks) {
-            const uint64_t da = make_desc(smem_u32(a_s) + ks * v.a_kadv, v.a_lbo, v.a_sbo, 2);
-            const uint64_t db = make_desc(smem_u32(b_s) + ks * v.b_kadv, v.b_lbo, v.b_sbo, 2);
+            const uint64_t da = make_desc(smem_u32(a_s) + ks * v.a_kadv, v.a_lbo, v.a_sbo, v.layout);
+            const uint64_t db = make_desc(smem_u32(b_s) + ks * v.b_kadv, v.b_lbo, v.b_sbo, v.layout);
             const uint32_t acc = ks > 0;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db),
@@ -115,11 +121,18 @@ int main() {
     //   "k-inner":  k groups contiguous (1024 B apart), mn blocks after all k groups      (A: 4 KB apart for K = 32)
     //   "mn-inner": mn blocks contiguous (1024 B apart), k groups after all mn blocks
     const int KG = K / 8;
+    const int MB_A = M / 32, MB_B = N / 32;       // 32-wide mn blocks
     struct { const char* name; Variant v; } tests[] = {
-        {"mn-inner  LBO=1024(mn)  SBO=mnblocks*1024(k)   adv=SBO", {1024, (M / 32) * 1024, 1024, (N / 32) * 1024, 1024, (M / 32) * 1024, 1024, (N / 32) * 1024, (M / 32) * 1024, (N / 32) * 1024}},
-        {"mn-inner  LBO/SBO swapped                      adv=kgrp", {(M / 32) * 1024, 1024, (N / 32) * 1024, 1024, 1024, (M / 32) * 1024, 1024, (N / 32) * 1024, (M / 32) * 1024, (N / 32) * 1024}},
-        {"k-inner   LBO=KG*1024(mn) SBO=1024(k)          adv=1024", {KG * 1024, 1024, KG * 1024, 1024, KG * 1024, 1024, KG * 1024, 1024, 1024, 1024}},
-        {"k-inner   LBO/SBO swapped                      adv=1024", {1024, KG * 1024, 1024, KG * 1024, KG * 1024, 1024, KG * 1024, 1024, 1024, 1024}},
+        // SWIZZLE_128B, 8-deep k atoms of 1024 B
+        {"SW128        mn-inner LBO=1024 SBO=mnblk*1024          ", {2, 1024, MB_A * 1024, 1024, MB_B * 1024, 1024, MB_A * 1024, 1024, MB_B * 1024, MB_A * 1024, MB_B * 1024}},
+        {"SW128        mn-inner LBO/SBO swapped                  ", {2, MB_A * 1024, 1024, MB_B * 1024, 1024, 1024, MB_A * 1024, 1024, MB_B * 1024, MB_A * 1024, MB_B * 1024}},
+        {"SW128        k-inner  LBO=KG*1024 SBO=1024             ", {2, KG * 1024, 1024, KG * 1024, 1024, KG * 1024, 1024, KG * 1024, 1024, 1024, 1024}},
+        {"SW128        k-inner  LBO/SBO swapped                  ", {2, 1024, KG * 1024, 1024, KG * 1024, KG * 1024, 1024, KG * 1024, 1024, 1024, 1024}},
+        // SWIZZLE_128B_BASE32B, 4-deep k atoms of 512 B; one MMA (k = 8) spans two atoms
+        {"SW128_BASE32 mn-inner LBO=512 SBO=mnblk*512 adv=2*SBO  ", {1, 512, MB_A * 512, 512, MB_B * 512, 512, MB_A * 512, 512, MB_B * 512, 2 * MB_A * 512, 2 * MB_B * 512}},
+        {"SW128_BASE32 mn-inner LBO/SBO swapped                  ", {1, MB_A * 512, 512, MB_B * 512, 512, 512, MB_A * 512, 512, MB_B * 512, 2 * MB_A * 512, 2 * MB_B * 512}},
+        {"SW128_BASE32 k-inner  LBO=2KG*512 SBO=512   adv=1024   ", {1, 2 * KG * 512, 512, 2 * KG * 512, 512, 2 * KG * 512, 512, 2 * KG * 512, 512, 1024, 1024}},
+        {"SW128_BASE32 k-inner  LBO/SBO swapped                  ", {1, 512, 2 * KG * 512, 512, 2 * KG * 512, 2 * KG * 512, 512, 2 * KG * 512, 512, 1024, 1024}},
     };
     for (auto& t : tests) {
         cudaMemset(d_out, 0xff, M * N * 4);
