@@ -28,8 +28,8 @@
 //   3      H0              W1h               [64,128) accumulate     +ray_bias1, relu      -> H1
 //   4      H1              W2 (3 -> N=16)    [0,16)                  +b2, sigmoid          -> rgb
 //
-// Roofline: per point 3 x (k_enc*64 + 64*nf + 64*128 + 64*64 + 64*16) MACs = 3 x 18 944 (nf = 64) on the tensor pipe
-// (2048 tf32 MAC / clk / SM -> 27.8 clk per point-layer-chain, 0.05 ms for 524 288 points) against
+// Roofline: per point 3 x (k_enc*64 + 64*nf + 64*128 + 64*64 + 64*16) MACs = 3 x 19 968 (k_enc = 40, nf = 64) on the
+// tensor pipe (2048 tf32 MAC / clk / SM -> 29.3 clk per point, 0.053 ms for 524 288 points on 148 SMs) against
 // (k_enc + 4) * 4 B = 176 B per point of HBM traffic without the training saves (0.014 ms) or + 1 KB with them.
 #include "common.cuh"
 #include "tc_common.cuh"
