@@ -43,7 +43,7 @@ def cpu_layers(monkeypatch):
             g[:, :relu_cols] = g[:, :relu_cols] * (relu_src[:, :relu_cols] > 0)
         dx[:, :k] = g
 
-    def bwd_weight(x2, ldx, dz, lddz, w, has_bias, n):
+    def bwd_weight(x2, ldx, dz, lddz, w, has_bias, n, w_sink=None, b_sink=None):
         n_out, k = w.shape
         calls.append(("bwd_weight", (n_out, k)))
         return dz[:, :n_out].t() @ x2[:, :k], (dz[:, :n_out].sum(0) if has_bias else None)
