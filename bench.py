@@ -420,7 +420,7 @@ def run_ours(args):
 
     # a whole reference training iteration: pixel pass + lidar pass, two (three) optimizer steps
     full = None
-    if not args.no_full_step:
+    if not args.no_full_step and world == 1:     # (one GPU only: an extra leg must not add collectives to a scaling run)
         try:
             full = time_full_step(tr, args, world, device, sync)
         except Exception as e:                       # an extra leg must never cost the headline numbers
