@@ -683,6 +683,8 @@ def parity_vs_oracle(tr, args):
         a, w = got[k].detach().double().cpu(), want[k].detach().double()
         if sel is not None:
             a, w = a[sel], w[sel]
+        if a.numel() == 0:
+            return None
         return float((a - w).abs().max() / want[k].detach().double().abs().max().clamp_min(1e-12))
 
     mse = float((got["rgb"].double().cpu() - want["rgb"].double()).square().mean())

@@ -257,6 +257,15 @@ def emer_linear_tc_bwd_weight(x, ldx, dz, lddz, dw, db, n, k, n_out, stream):
     _bwd_weight(_view(x, n, k, ldx), _view(dz, n, n_out, lddz), _view(dw, n_out, k), _vec(db, n_out))
 
 
+def emer_linear_tc_bwd_weight_mn(x, ldx, dz, lddz, dw, db, n, k, n_out, stream):
+    if n == 0:
+        return
+    _require(n_out == 64 and 4 <= k <= 128, f"emer_linear_tc_bwd_weight_mn: shape k={k} n_out={n_out} (need n_out = 64, k <= 128)")
+    _require(ldx % 4 == 0 and lddz % 4 == 0 and _aligned16(x, dz) and (k + 3) // 4 * 4 <= ldx,
+             "emer_linear_tc_bwd_weight_mn: rows must be 16-byte aligned")
+    _bwd_weight(_view(x, n, k, ldx), _view(dz, n, n_out, lddz), _view(dw, n_out, k), _vec(db, n_out))
+
+
 def emer_linear_narrow_bwd_weight(x, ldx, dz, lddz, dw, db, n, k, n_out, stream):
     _check_narrow(k, n_out, "emer_linear_narrow_bwd_weight")
     _bwd_weight(_view(x, n, k, ldx), _view(dz, n, n_out, lddz), _view(dw, n_out, k), _vec(db, n_out))

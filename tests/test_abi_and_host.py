@@ -195,3 +195,29 @@ def test_tensor_core_eligibility_mirrors_the_library_limits():
             except RuntimeError:
                 lib_ok = False
             assert lib_ok == _ops._tc_wgrad_fits(k, n_out), (k, n_out)
+
+
+def test_blur_stepfun_merge_equals_the_reference_sort():
+    """The merge formulation of blur_stepfun (two searchsorted ranks + scatter) gives the reference's sort-based result
+    (nerfacc_prop_net.py:22-34), ties included."""
+    import torch
+
+    from emernerf_b200.third_party.nerfacc_prop_net import blur_stepfun
+
+    def reference(x, y, r):
+        xr, xr_idx = torch.sort(torch.cat([x - r, x + r], dim=-1))
+        y1 = (torch.cat([y, torch.zeros_like(y[..., :1])], dim=-1) - torch.cat([torch.zeros_like(y[..., :1]), y], dim=-1)) / (2 * r)
+        y2 = torch.cat([y1, -y1], dim=-1).take_along_dim(xr_idx[..., :-1], dim=-1)
+        yr = torch.cumsum((xr[..., 1:] - xr[..., :-1]) * torch.cumsum(y2, dim=-1), dim=-1).clamp_min(0)
+        return xr, torch.cat([torch.zeros_like(yr[..., :1]), yr], dim=-1)
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.sort(torch.rand(33, 65, generator=g), dim=-1).values
+    x[:, 10] = x[:, 9]                      # repeated edges
+    x[0] = torch.linspace(0, 1, 65)         # regular spacing: x_i - r == x_j + r ties for r = k / 128
+    y = torch.rand(33, 64, generator=g)
+    for r in (0.03, 0.003, 1.0 / 128):
+        e0, h0 = reference(x, y, r)
+        e1, h1 = blur_stepfun(x, y, r)
+        assert torch.equal(e0, e1)
+        assert torch.allclose(h0, h1, rtol=1e-6, atol=1e-7)

@@ -115,6 +115,9 @@ def _tols(mode):
     tol = {"*": TOL, "median_depth": 5e-2}                   # median: index flip at cw == 0.5
     for k in EXTRAS:
         tol[k] = 1e-3 if k in ("weights", "trans") else 2e-2
+    # depth of the static-only / dynamic-only compositing (decomposition outputs): its own weights, its own small
+    # opacities in the denominator -- the stability mask is about the joint density's samples; 1e-4 with pinned samples
+    tol["static_depth"] = tol["dynamic_depth"] = 1e-2
     return tol
 
 

@@ -528,13 +528,13 @@ def test_field_chain_forward_backward_vs_fp64(k_enc, n_feat, n, S, c):
         assert rel_err(sem, want[3]) < 2e-5
     else:
         assert sem is None
+    saved = [t.clone() for t in sigma.grad_fn.saved_tensors[:4]]        # enc, hb, [h0 | geo], h1 (freed by the backward pass)
     # gradients: a scalar that touches every output
     g_s, g_c, g_g = rnd(n), rnd(n, 3), rnd(n, 64, scale=0.1)
     loss = (sigma * g_s).sum() + (rgb * g_c).sum() + (geo * g_g).sum() + (0 if sem is None else (sem * g_g).sum())
     got = torch.autograd.grad(loss, [enc, rb] + ws)
     enc64, rb64 = enc.detach().double().requires_grad_(True), rb.detach().double().requires_grad_(True)
     ws64 = [w.detach().double().requires_grad_(True) for w in ws]
-    saved = sigma.grad_fn.saved_tensors                        # enc, hb, [h0 | geo], h1, ...
     masks = [(saved[1] > 0).double(), (saved[2][:, :64] > 0).double(), (saved[3] > 0).double()]
     for got_act, want_act in ((saved[1], want[4]), (saved[2][:, :64], want[5]), (saved[3], want[6])):
         assert rel_err(got_act, want_act) < 2e-5               # what the backward pass reads
@@ -631,3 +631,28 @@ def test_gen_rays_matches_the_reference_formula():
     assert torch.equal(o2, out["origins"]) and torch.equal(d2, out["viewdirs"]) and torch.equal(n2, out["direction_norms"])
     # unit directions
     assert float((out["viewdirs"].norm(dim=-1) - 1).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("k,n,ldx,lddz", [(64, 64 * 1500 + 21, 64, 64), (40, 128 * 700 + 5, 40, 64), (128, 64 * 900 + 63, 128, 64),
+                                          (64, 37, 128, 128), (100, 64 * 400, 104, 64), (64, 524288, 128, 128)])
+def test_weight_gradient_mn_major_operands(k, n, ldx, lddz):
+    """emer_linear_tc_bwd_weight_mn (csrc/wgrad_mn.cu: operands as they lie in memory, MN-major SWIZZLE_128B_BASE32B,
+    elementwise hi / lo split) against fp64: dW and db within 2e-5 of the sum over all rows; ragged last tile, strided
+    rows, k not a multiple of 32, accumulation into a non-zero buffer."""
+    import ctypes
+
+    from emernerf_b200 import _lib, _ops
+
+    g = torch.Generator(device=DEV).manual_seed(k + n)
+    xb = torch.randn(n, ldx, device=DEV, generator=g)
+    zb = torch.randn(n, lddz, device=DEV, generator=g)
+    x, dz = xb[:, :k], zb[:, :64]
+    dw0, db0 = torch.randn(64, k, device=DEV, generator=g), torch.randn(64, device=DEV, generator=g)
+    dw, db = dw0.clone(), db0.clone()
+    _ops._need_cuda(x)
+    _lib.call("emer_linear_tc_bwd_weight_mn", _ops._ptr(x), ldx, _ops._ptr(dz), lddz, _ops._ptr(dw), _ops._ptr(db), n, k, 64,
+              _ops._stream())
+    want_w = dw0.double() + dz.double().T @ x.double()
+    want_b = db0.double() + dz.double().sum(0)
+    assert rel_err(dw, want_w) < 2e-5, rel_err(dw, want_w)
+    assert rel_err(db, want_b) < 2e-5, rel_err(db, want_b)
