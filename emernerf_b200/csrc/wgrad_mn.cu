@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_mn_kernel(const Params p) {
     uint64_t* full_bar = bars;                 // [STAGES]
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES);
-    float* red = reinterpret_cast<float*>(bars + 2 * STAGES + 1);   // [NCONV * 4] bias partial sums
+    float* red = reinterpret_cast<float*>(bars + 2 * STAGES + 2);   // [NCONV * 4] bias partial sums (16-byte aligned:
+                                                                    // (2 STAGES + 2) * 8 is a multiple of 16)
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool is_issuer = warp == NCONV / 32;
