@@ -418,6 +418,11 @@ def run_ours(args):
                "h2d_bytes_per_step": tr.h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}
 
+    # per-kernel device times: CUDA events around every library launch over 3 eager steps, same
+    # process / inputs / clocks, right after the timed region (a replayed graph cannot be event-timed
+    # per kernel).  The ncu launch list under profiles/ must agree on the kernel's SHARE.
+    table = kernel_table(tr, sync, steps=3)          # every rank runs it (the steps all-reduce)
+
     # a whole reference training iteration: pixel pass + lidar pass, two (three) optimizer steps
     full = None
     if not args.no_full_step and world == 1:     # (one GPU only: an extra leg must not add collectives to a scaling run)
@@ -427,10 +432,6 @@ def run_ours(args):
             full = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.synchronize()
 
-    # per-kernel device times: CUDA events around every library launch over 3 eager steps, same
-    # process / inputs / clocks, right after the timed region (a replayed graph cannot be event-timed
-    # per kernel).  The ncu launch list under profiles/ must agree on the kernel's SHARE.
-    table = kernel_table(tr, sync, steps=3)          # every rank runs it (the steps all-reduce)
 
     if args.profile_all and tr.use_graph and hasattr(tr, "graphs"):
         for prg in (False, True):               # device time of each captured branch of the step

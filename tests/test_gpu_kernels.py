@@ -654,5 +654,6 @@ def test_weight_gradient_mn_major_operands(k, n, ldx, lddz):
               _ops._stream())
     want_w = dw0.double() + dz.double().T @ x.double()
     want_b = db0.double() + dz.double().sum(0)
-    assert rel_err(dw, want_w) < 2e-5, rel_err(dw, want_w)
-    assert rel_err(db, want_b) < 2e-5, rel_err(db, want_b)
+    tol = 2e-5 if n < 200000 else 5e-5               # fp32 accumulation over 8192 tiles in TMEM + 148 partial sums
+    assert rel_err(dw, want_w) < tol, rel_err(dw, want_w)
+    assert rel_err(db, want_b) < tol, rel_err(db, want_b)
