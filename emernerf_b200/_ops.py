@@ -24,7 +24,8 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 # fp32 CUDA-core kernels of linear_simt.cu (the bit-faithful checker); both are sm_100a code in the
 # same library -- this is a debugging switch, not a backend dispatch.
 LINEAR_IMPL = os.environ.get("EMER_LINEAR", "tc")
-LINEAR_WGRAD_IMPL = os.environ.get("EMER_LINEAR_WGRAD", "tc")      # "mn": MN-major operands (csrc/wgrad_mn.cu); "simt"
+LINEAR_WGRAD_IMPL = os.environ.get("EMER_LINEAR_WGRAD", "mn")      # "mn": MN-major operands (csrc/wgrad_mn.cu) where the shape
+                                                                   # allows, else "tc" (transposing, linear_tc.cu); "simt"
 SKIP_BWD_IMPL = os.environ.get("EMER_SKIP_BWD", "stack")   # "stack": one stacked product; "add": two + add
 TC_MIN_ROWS = 1024          # tiny per-ray heads are launch-bound either way
 STOT_KINDS = {"uniform": 0, "lindisp": 1, "sqrt": 2, "log": 3, "uniform_lindisp": 4, "uniform_lindisp_0": 5}
@@ -101,11 +102,11 @@ def _grad_sink(t: Optional[Tensor]):
 
 
 # ----------------------------------------------------------------------------- weight gradients on a side stream
-# EMER_WGRAD_STREAM=1: the fused chain's weight-gradient kernels run on a side stream, forked where the dZ buffers are
+# (EMER_WGRAD_STREAM=0 turns it off.)  With FusedAdam's gradient sinks the fused chain's weight-gradient kernels run on a side stream, forked where the dZ buffers are
 # complete.  The main stream goes on to the hash-grid scatter and -- multi-GPU -- to the reduce-scatter of the table
 # gradients, which no weight gradient feeds; the optimizer (or the reduction of the MLP gradients) joins the side stream
 # first (:func:`join_side_streams`).  Captured into the step's CUDA graph this becomes two parallel branches.
-WGRAD_STREAM = os.environ.get("EMER_WGRAD_STREAM", "0") == "1"
+WGRAD_STREAM = os.environ.get("EMER_WGRAD_STREAM", "1") == "1"
 _SIDE: Dict[int, "torch.cuda.Stream"] = {}
 _PENDING: Dict[int, bool] = {}
 _AFTER_JOIN: list = []          # small updates of buffers the main stream also writes: run there, after the join
@@ -659,7 +660,7 @@ def field_tail(feats: Tensor, dirs: Tensor, idx: Optional[Tensor], emb: Optional
 
 # ----------------------------------------------------------------------------- fused field chain
 FIELD_CHAIN = os.environ.get("EMER_FIELD_CHAIN", "fused")      # "layers": the per-layer path (A/B and debugging switch)
-CHAIN_BWD = os.environ.get("EMER_CHAIN_BWD", "layers")          # "layers": data gradients layer by layer (A/B switch)
+CHAIN_BWD = os.environ.get("EMER_CHAIN_BWD", "fused")          # "layers": data gradients layer by layer (A/B switch)
 CHAIN_K_ENC = (32, 40, 64)
 
 
