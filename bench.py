@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--dp-mode", default="sharded", choices=["sharded", "allreduce"],
                     help="multi-GPU gradient exchange (emernerf_b200.distributed): reduce-scatter + sharded Adam + "
                          "all-gather, or all-reduce + replicated Adam")
+    ap.add_argument("--no-defer-gather", action="store_true",
+                    help="issue the field's parameter all-gather right after its Adam step instead of beside the next "
+                         "step's proposal sampling")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --rays per GPU; strong: --rays in total, split over the GPUs (BASELINE configs[3,4])")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying "
@@ -184,7 +187,9 @@ class Trainer:
     def sync_and_step(self, opt, params):
         """Average the gradients over the ranks and take the optimizer step."""
         if self.dp is not None:
-            self.dp.step(opt)                     # one flat collective per group (emernerf_b200/distributed.py)
+            # one flat collective per group (emernerf_b200/distributed.py); the field's parameter all-gather is deferred
+            # to the start of the next step, where it runs beside the proposal sampling
+            self.dp.step(opt, defer_gather=(opt is self.opt and not self.args.no_defer_gather))
             return
         if self.world > 1:
             import torch.distributed as dist
@@ -249,6 +254,8 @@ class Trainer:
     def _lidar_body(self, batch, prg):
         from emernerf_b200.radiance_fields.render_utils import render_rays
 
+        if self.dp is not None:
+            self.dp.start_deferred()
         out = render_rays(self.field, self.est, self.props, batch, self.cfg, proposal_requires_grad=prg, prefix="lidar_")
         if prg:
             ploss = self.est.compute_loss(out["extras"]["trans"], 1024.0)
@@ -282,6 +289,8 @@ class Trainer:
     def _step_body(self, batch, prg):
         from emernerf_b200.radiance_fields.render_utils import render_rays
 
+        if self.dp is not None:
+            self.dp.start_deferred()
         out = render_rays(self.field, self.est, self.props, batch, self.cfg, proposal_requires_grad=prg)
         if prg:
             ploss = self.est.compute_loss(out["extras"]["trans"], 1024.0)

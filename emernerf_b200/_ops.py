@@ -136,6 +136,16 @@ class _on_side_stream:
         return self.ctx.__exit__(*exc)
 
 
+_BEFORE_FIELD: list = []        # streams whose work the field forward needs (a deferred parameter all-gather)
+
+
+def join_before_field() -> None:
+    """Called by RadianceField.forward: the current stream waits for work that only the FIELD's parameters depend on
+    (DataParallel's deferred all-gather runs beside the proposal sampling of the next step)."""
+    while _BEFORE_FIELD:
+        torch.cuda.current_stream().wait_stream(_BEFORE_FIELD.pop())
+
+
 def join_side_streams() -> None:
     """The current stream waits for weight gradients still running on a side stream (no-op when there are none)."""
     for idx, pending in list(_PENDING.items()):

@@ -39,6 +39,8 @@ class DataParallel:
         self.native = self.on and dist.get_backend(group) == "nccl"
         self.optimizers = list(optimizers)
         self.mode = mode
+        self._deferred: List[FusedAdam] = []
+        self._comm = None
         if self.on and mode == "sharded":
             for opt in self.optimizers:
                 for g in opt._groups:
@@ -96,11 +98,39 @@ class DataParallel:
                 dist.all_gather(parts, g.flat_params[lo:hi].contiguous(), group=self.group)
                 g.flat_params.copy_(torch.cat(parts))
 
-    def step(self, opt: FusedAdam) -> None:
-        """reduce -> Adam -> gather: what replaces ``optimizer.step()`` after ``backward()``."""
+    def step(self, opt: FusedAdam, defer_gather: bool = False) -> None:
+        """reduce -> Adam -> gather: what replaces ``optimizer.step()`` after ``backward()``.
+
+        ``defer_gather`` (sharded mode, for the FIELD's optimizer): the all-gather of the updated parameters is not
+        issued here but by :meth:`start_deferred` at the beginning of the next step, on a side stream -- the proposal
+        sampling that opens a step reads only the proposal networks, so the gather runs beside it and
+        ``RadianceField.forward`` joins it (``_ops.join_before_field``)."""
         self.reduce(opt)
         opt.step()
-        self.gather(opt)
+        if defer_gather and self.on and self.mode == "sharded":
+            self._deferred.append(opt)
+        else:
+            self.gather(opt)
+
+    def start_deferred(self) -> None:
+        """Issue the deferred all-gathers on the communication stream (call first thing in a step)."""
+        if not self._deferred:
+            return
+        dev = self._deferred[0]._groups[0].grad.device
+        if dev.type != "cuda":                     # (gloo host-logic tests: no streams)
+            for opt in self._deferred:
+                self.gather(opt)
+            self._deferred = []
+            return
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        self._comm.wait_stream(main)
+        with torch.cuda.stream(self._comm):
+            for opt in self._deferred:
+                self.gather(opt)
+        self._deferred = []
+        _ops._BEFORE_FIELD.append(self._comm)
 
     def bytes_per_step(self, opt: FusedAdam) -> int:
         """Bytes each rank sends per step for ``opt`` (ring algorithms: 2 (w-1)/w of the flat size in both modes)."""

@@ -330,6 +330,7 @@ class RadianceField(nn.Module):
         query_pe_head: bool = True,
     ) -> Dict[str, Tensor]:
         out: Dict[str, Tensor] = {}
+        _ops.join_before_field()               # (multi-GPU: a parameter all-gather may still be running beside the sampling)
         G, S = self.geometry_feature_dim, self.semantic_feature_dim
         tail = None if (return_density_only or positions.dim() != 3) else self._tail_inputs(directions, data_dict)
         # the fused chain (base MLP + density + colour head in one tcgen05 kernel) when the model has its shape

@@ -53,18 +53,26 @@ def main():
     props = [p.to(dev).train() for p in props]
     est = PropNetEstimator(None, None).to(dev).train()
     opt = FusedAdam(field.parameters(), flatten_params=True, **ADAM)
-    dp = DataParallel([opt], mode="sharded" if mode == "single" else mode)
+    defer = mode == "sharded_defer"
+    dp = DataParallel([opt], mode="sharded" if mode in ("single", "sharded_defer") else mode)
 
     n = cases.N_RAYS // world
     sl = slice(rank * n, (rank + 1) * n)
     batch = {k: v[sl].to(dev) for k, v in g.tensors("in/pixel").items()}
     est._jitter_override = [j[sl].to(dev) for j in g.jitters("train")]
     for step in range(2):
+        dp.start_deferred()
         out = render_rays(field, est, props, batch, cases.render_cfg(), proposal_requires_grad=False)
         loss = ((out["rgb"] - batch["pixels"]) ** 2).mean() + 0.01 * out["depth"].mean()
         opt.zero_grad()
         loss.backward()
-        dp.step(opt)
+        dp.step(opt, defer_gather=defer)
+    dp.start_deferred()
+    if device != "cpu":
+        from emernerf_b200 import _ops
+
+        _ops.join_before_field()
+        torch.cuda.synchronize()
     if rank == 0:
         torch.save({k: v.detach().cpu() for k, v in field.state_dict().items()}, out_path)
     if world > 1:

@@ -48,7 +48,7 @@ def test_data_parallel_steps_equal_the_full_batch_step(tmp_path):
     optimizer steps on half batches -- all-reduce of the flat gradient, and reduce-scatter -> sharded Adam -> all-gather
     of the flat parameters -- leave every parameter where the one-process full-batch steps leave it."""
     single = _run_dp("cpu", "single", 1, str(tmp_path / "single.pt"))
-    for mode in ("allreduce", "sharded"):
+    for mode in ("allreduce", "sharded", "sharded_defer"):
         got = _run_dp("cpu", mode, 2, str(tmp_path / f"{mode}.pt"))
         for k, v in single.items():
             if "sky_head" in k:          # gradient ~ (1 - opacity) = rounding noise in this scene, Adam makes it +-lr

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_rank_nccl_steps_equal_the_full_batch_step(tmp_path):
     single = _run_dp("cuda", "single", 1, str(tmp_path / "single.pt"))
-    for mode in ("allreduce", "sharded"):
+    for mode in ("allreduce", "sharded", "sharded_defer"):
         got = _run_dp("cuda", mode, 2, str(tmp_path / f"{mode}.pt"))
         for k, v in single.items():
             if "sky_head" in k:

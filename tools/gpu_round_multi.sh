@@ -13,8 +13,8 @@ for mode in sharded allreduce; do
 done
 timeout 600 bash -c "$(declare -f run); N=$N run 296$((RANDOM % 90 + 10)) --optimizer torch" > gpurun_out/bench_n${N}_torch_$tag.log 2> gpurun_out/bench_n${N}_torch_$tag.err
 echo "torch arm: $(head -c 260 gpurun_out/bench_n${N}_torch_$tag.log)"
-EMER_WGRAD_STREAM=0 timeout 600 bash -c "$(declare -f run); N=$N run 297$((RANDOM % 90 + 10)) --dp-mode sharded" > gpurun_out/bench_n${N}_noside_$tag.log 2> gpurun_out/bench_n${N}_noside_$tag.err
-echo "sharded, no side stream: $(head -c 260 gpurun_out/bench_n${N}_noside_$tag.log)"
+timeout 600 bash -c "$(declare -f run); N=$N run 297$((RANDOM % 90 + 10)) --dp-mode sharded --no-defer-gather" > gpurun_out/bench_n${N}_nodefer_$tag.log 2> gpurun_out/bench_n${N}_nodefer_$tag.err
+echo "sharded, gather not deferred: $(head -c 260 gpurun_out/bench_n${N}_nodefer_$tag.log)"
 if [ "$N" = "8" ]; then
   timeout 600 bash -c "$(declare -f run); N=$N run 298$((RANDOM % 90 + 10)) --scaling strong --rays 16384 --variant flow" > gpurun_out/bench_n${N}_strong_flow_$tag.log 2> gpurun_out/bench_n${N}_strong_flow_$tag.err
   echo "strong flow 16384: $(head -c 300 gpurun_out/bench_n${N}_strong_flow_$tag.log)"
