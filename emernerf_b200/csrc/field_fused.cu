@@ -18,8 +18,10 @@
 // (B operands) are resident in shared memory as tf32 hi / lo panels.  ACTIVATIONS LIVE IN TENSOR MEMORY: the epilogue of
 // layer i reads its accumulator with tcgen05.ld, applies bias / ReLU, splits into tf32 hi + lo and writes them back with
 // tcgen05.st as the A operand of layer i+1 (tcgen05.mma with A in TMEM), so no activation ever touches shared memory.
-// Two warpgroups own two tiles in flight (256 TMEM columns each: 128 operand + 128 accumulator); one warp issues the
-// MMAs for both, alternating, so one tile's MMAs run under the other tile's epilogue.
+// Two tiles are in flight (256 TMEM columns each: 128 operand + 128 accumulator), each served by two warpgroups that take
+// the two 32-column halves of every 64-column block (the per-stage TMEM -> registers -> TMEM round trip is the serial part
+// of a tile's chain: with one thread per whole row the tensor pipe sat idle 70 % of the time); one warp issues the MMAs for
+// both tiles, alternating, so one tile's MMAs run under the other tile's epilogue.
 //
 //   stage  A (TMEM)        B (smem)          D (TMEM)                epilogue
 //   0      enc hi/lo       Wb0 [64 x k_enc]  [0,64)                  +bb0, relu            -> Hb
@@ -40,8 +42,10 @@ namespace ff {
 using namespace emer::tc;
 
 constexpr int ROWS = 128;
-constexpr int EPI_THREADS = 256;              // two warpgroups of 4 warps: warp w owns TMEM lanes 32 (w % 4) ..
+constexpr int EPI_THREADS = 512;              // two tiles in flight x two warpgroups per tile (each takes half of the columns);
+                                              // warp w owns TMEM lanes 32 (w % 4) .. of its tile
 constexpr int THREADS = EPI_THREADS + 32;     // + the MMA-issuing warp
+constexpr int TILE_THREADS = EPI_THREADS / 2; // epilogue threads per tile (arrivals per operand barrier)
 constexpr int H = 64;                         // hidden / geometry / head width this kernel is specialised for
 
 struct FwdParams {
@@ -122,8 +126,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
     const bool is_issuer = warp == EPI_THREADS / 32;
 
     if (tid == 0) {
-        mbar_init(&a_full[0], ROWS);
-        mbar_init(&a_full[1], ROWS);
+        mbar_init(&a_full[0], TILE_THREADS);
+        mbar_init(&a_full[1], TILE_THREADS);
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -203,8 +207,11 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             }
         }
     } else {
-        // ================= epilogue warpgroups: one point per thread, the point's row is this thread's TMEM lane
-        const int wg = tid >> 7;
+        // ================= epilogue warpgroups: a point's row is its thread's TMEM lane; the two warpgroups of a tile take
+        // the two 32-column halves of every 64-column block (16-column chunks 2 half, 2 half + 1), so a stage's
+        // TMEM -> registers -> TMEM round trip is half as long as with one thread per whole row
+        const int wg = tid >> 8;                 // tile slot
+        const int half = (tid >> 7) & 1;         // column half
         const int r_in = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(wg * 256);
@@ -222,7 +229,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             const bool ok = tile < n_tiles && row < p.n;
             const float4* src = reinterpret_cast<const float4*>(p.enc + (ok ? row : 0) * p.ld_enc);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) x_next[q] = ok ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < NQ; ++q)
+                if (((q >> 1) & 1) == half) x_next[q] = ok ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         load_enc((int64_t)blockIdx.x * 2 + wg);
 
@@ -236,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             // ---- stage 0 operand: enc row -> tf32 hi / lo in TMEM
 #pragma unroll
             for (int c = 0; c < K_ENC / 8; ++c) {
-                {
+                if ((c & 1) == half) {
                     const float4 u0 = x_next[2 * c], u1 = x_next[2 * c + 1];
                     const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
                     uint32_t hi[8], lo[8];
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + (uint32_t)(c * 16), r);
                 tmem_ld_wait();
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + (uint32_t)(c * 16), r);
                 tmem_ld_wait();
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             }
             if (p.n_feat > H) {
 #pragma unroll
-                for (int c = 4; c < 8; ++c) {
+                for (int c = 4 + 2 * half; c < 6 + 2 * half; ++c) {
                     uint32_t r[16];
                     tmem_ld16(d_addr + (uint32_t)(c * 16), r);
                     tmem_ld_wait();
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + (uint32_t)(c * 16), r);
                 float b[16];
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + 64u + (uint32_t)(c * 16), r);
                 float b[16];
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             // ---- stage 5: rgb = sigmoid(D[0,3) + b2)
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
-            {
+            if (half == 0) {
                 uint32_t r[4];
                 tmem_ld4(d_addr, r);
                 tmem_ld_wait();
@@ -447,14 +455,14 @@ __device__ __forceinline__ void stage_weight_t(uint8_t* hi, uint8_t* lo, const f
     (void)kpad;
 }
 
-// bit j of the result: x[j] > 0 for the 64 floats of one saved activation row
-__device__ __forceinline__ uint64_t relu_mask64(const float* __restrict__ row, bool ok) {
-    uint64_t m = 0;
+// bit j of the result: x[j] > 0 for 32 floats of one saved activation row
+__device__ __forceinline__ uint32_t relu_mask32(const float* __restrict__ row, bool ok) {
+    uint32_t m = 0;
     if (ok) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < 8; ++q) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(row) + q);
-            m |= (uint64_t)((t.x > 0.f) | ((t.y > 0.f) << 1) | ((t.z > 0.f) << 2) | ((t.w > 0.f) << 3)) << (4 * q);
+            m |= (uint32_t)((t.x > 0.f) | ((t.y > 0.f) << 1) | ((t.z > 0.f) << 2) | ((t.w > 0.f) << 3)) << (4 * q);
         }
     }
     return m;
@@ -510,8 +518,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
     const bool is_issuer = warp == EPI_THREADS / 32;
 
     if (tid == 0) {
-        mbar_init(&a_full[0], ROWS);
-        mbar_init(&a_full[1], ROWS);
+        mbar_init(&a_full[0], TILE_THREADS);
+        mbar_init(&a_full[1], TILE_THREADS);
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -583,7 +591,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
         }
     } else {
-        const int wg = tid >> 7;
+        const int wg = tid >> 8;                 // tile slot
+        const int half = (tid >> 7) & 1;         // column half (see field_fwd_kernel)
         const int r_in = tid & 127;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(wg * 256);
@@ -602,8 +611,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             const int64_t ray = (tile * ROWS + (r_in & ~31)) / p.samples;
             const bool warp_live = tile * ROWS + (r_in & ~31) < p.n;
 
-            // ---- stage 0 operand: dZ2 = d_rgb * rgb (1 - rgb), 3 columns of an 8-wide k step
-            {
+            // ---- stage 0 operand: dZ2 = d_rgb * rgb (1 - rgb), 3 columns of an 8-wide k step (written by half 0)
+            if (half == 0) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) hi[j] = lo[j] = 0u;
@@ -627,17 +636,17 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             mbar_arrive(&a_full[wg]);
 
             // ---- stage 0 result: dZ1 = dH1 * (h1 > 0)
-            uint64_t mask = relu_mask64(p.h1 + rsafe * H, row_ok);
+            uint32_t mask = relu_mask32(p.h1 + rsafe * H + half * 32, row_ok);        // columns 32 half .. 32 half + 31
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + (uint32_t)(c * 16), r);
                 tmem_ld_wait();
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c * 16 + j)) & 1ull) ? __uint_as_float(r[j]) : 0.0f;
+                for (int j = 0; j < 16; ++j) v[j] = ((mask >> ((c & 1) * 16 + j)) & 1u) ? __uint_as_float(r[j]) : 0.0f;
                 if (row_ok) store16(p.dz1 + row * H + c * 16, v);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
@@ -654,17 +663,17 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             mbar_arrive(&a_full[wg]);
 
             // ---- stage 1 result: dZ0 = dH0 * (h0 > 0)   (dG stays in the accumulator's upper half)
-            mask = relu_mask64(p.hg + rsafe * 128, row_ok);
+            mask = relu_mask32(p.hg + rsafe * 128 + half * 32, row_ok);
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + (uint32_t)(c * 16), r);
                 tmem_ld_wait();
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c * 16 + j)) & 1ull) ? __uint_as_float(r[j]) : 0.0f;
+                for (int j = 0; j < 16; ++j) v[j] = ((mask >> ((c & 1) * 16 + j)) & 1u) ? __uint_as_float(r[j]) : 0.0f;
                 if (row_ok) store16(p.d1 + row * 128 + c * 16, v);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
@@ -686,7 +695,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + 64u + (uint32_t)(c * 16), r);
                 float g[16];
@@ -719,7 +728,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
                 mbar_wait(&d_full[wg], ph); ph ^= 1u;           // (the first piece's MMAs have read the operand)
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 2 * half; c < 2 * half + 2; ++c) {
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = 0.0f;
@@ -741,17 +750,17 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
 
             // ---- stage 3 result: dZb = dHb * (hb > 0)
-            mask = relu_mask64(p.hb + rsafe * H, row_ok);
+            mask = relu_mask32(p.hb + rsafe * H + half * 32, row_ok);
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * half; c < 2 * half + 2; ++c) {
                 uint32_t r[16];
                 tmem_ld16(d_addr + (uint32_t)(c * 16), r);
                 tmem_ld_wait();
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = ((mask >> (c * 16 + j)) & 1ull) ? __uint_as_float(r[j]) : 0.0f;
+                for (int j = 0; j < 16; ++j) v[j] = ((mask >> ((c & 1) * 16 + j)) & 1u) ? __uint_as_float(r[j]) : 0.0f;
                 if (row_ok) store16(p.dzb + row * H + c * 16, v);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
@@ -767,7 +776,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             tc_fence_after();
             if (p.d_enc) {
 #pragma unroll
-                for (int c = 0; c < K_ENC / 8; ++c) {
+                for (int c = half; c < K_ENC / 8; c += 2) {
                     uint32_t r[8];
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])

@@ -357,14 +357,26 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(const float* __restri
 #pragma unroll
     for (int o = 0; o < NARROW_MAX_OUT; ++o) acc[o] = bacc[o] = 0.0f;
     if (rl < lanes) {
-        for (int64_t row = r0 + rl; row < r1; row += lanes) {
-            const float xv = c < k ? __ldg(x + row * ldx + c) : 0.0f;
+        // four rows per trip: the loads of a trip are independent, so four row fetches are in flight per thread (the
+        // one-row loop was latency-bound: 0.10 ms for 64 -> 3 over 524 288 rows against 0.02 ms of HBM time)
+        constexpr int U = 4;
+        for (int64_t row = r0 + rl; row < r1; row += (int64_t)lanes * U) {
+            float xv[U], g[U][NARROW_MAX_OUT];
 #pragma unroll
-            for (int o = 0; o < NARROW_MAX_OUT; ++o) {
-                if (o < n_out) {
-                    const float g = __ldg(dz + row * lddz + o);      // broadcast within the warp
-                    acc[o] = fmaf(g, xv, acc[o]);
-                    if (c == 0) bacc[o] += g;
+            for (int u = 0; u < U; ++u) {
+                const int64_t rr = row + (int64_t)u * lanes;
+                const bool ok = rr < r1;
+                xv[u] = (ok && c < k) ? __ldg(x + rr * ldx + c) : 0.0f;
+#pragma unroll
+                for (int o = 0; o < NARROW_MAX_OUT; ++o)
+                    g[u][o] = (ok && o < n_out) ? __ldg(dz + rr * lddz + o) : 0.0f;      // broadcast within the warp
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int o = 0; o < NARROW_MAX_OUT; ++o) {
+                    acc[o] = fmaf(g[u][o], xv[u], acc[o]);
+                    if (c == 0) bacc[o] += g[u][o];
                 }
             }
         }

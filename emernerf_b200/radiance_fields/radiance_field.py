@@ -491,7 +491,7 @@ class RadianceField(nn.Module):
         dd = self.direction_encoding(d).to(directions)
         emb = self._appearance(directions, data_dict)
         if emb is not None:
-            dd = torch.cat([dd, emb], dim=-1)
+            dd = _ops.cat_pad4([dd, emb])              # 49 columns in 52-float rows: the tensor-core loaders want 16-byte rows
         results = {"rgb_sky": self.sky_head(dd, out_act=_ops.ACT_SIGMOID)}
         if self.enable_feature_head:
             # (the reference evaluates dino_sky_head twice and discards the first result, Q9)
