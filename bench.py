@@ -493,8 +493,16 @@ def run_ours(args):
                   file=sys.stderr)
         print(f"# library kernels: {tot_ms / 3:.3f} ms/step of {ms / args.steps:.3f} ms/step", file=sys.stderr)
 
-    # measured per launch by `ncu --set full` (profiles/r1_grid_ncu_full_summary.csv): dram read + write
-    GRID_FWD_DRAM_TRAFFIC = {"D3L10F4_N524288": 266852096 + 92160256}
+    # DRAM bytes per launch and tensor-pipe activity measured by `ncu --set full` on this build's kernels
+    # (profiles/r2_dram_traffic.json, extracted from the reports summarised in profiles/r2_*_ncu_summary.md)
+    try:
+        NCU = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")))
+    except Exception:
+        NCU = {}
+
+    def measured(name, tag):
+        e = NCU.get(f"{name}[{tag}]") or NCU.get(name) or {}
+        return e.get("traffic"), e.get("tensor_pipe_active_pct")
 
     def layer_bytes(name, tag):
         """Algorithmic HBM bytes of one dense-layer launch: rows * (inputs + outputs) * 4."""
@@ -509,24 +517,28 @@ def run_ours(args):
     def roofline_of(key):
         name, tag = key
         avg_ms = per_launch[key]
+        traffic = measured(name, tag)[0]
         if name == "emer_grid_fwd":
-            nbytes, traffic = _lib.algorithmic_bytes(tag), GRID_FWD_DRAM_TRAFFIC.get(tag)
+            nbytes = _lib.algorithmic_bytes(tag)
         elif name == "emer_grid_bwd":
             # scatter: the corners are read-modify-written (2x the corner bytes), dy read once
             import re
 
             m = re.match(r"D(\d+)L(\d+)F(\d+)_N(\d+)", tag)
             d_, l_, f_, n_ = (int(v) for v in m.groups())
-            nbytes, traffic = n_ * (2 * l_ * (2 ** d_) * f_ * 4 + d_ * 4 + l_ * f_ * 4), None
+            nbytes = n_ * (2 * l_ * (2 ** d_) * f_ * 4 + d_ * 4 + l_ * f_ * 4)
         elif name.startswith("emer_linear"):
-            nbytes, traffic = layer_bytes(name, tag), None
+            nbytes = layer_bytes(name, tag)
         else:
             return None
         if not nbytes:
             return None
         ach = nbytes / (avg_ms / 1e3) / 1e9
         return {"kernel": f"{name}[{tag}]", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": ach / hbm_peak, "traffic": traffic,
+                # what actually crossed the DRAM pins (ncu) over the same time: the L2 serves the rest of the algorithmic bytes
+                "dram_frac": (traffic / (avg_ms / 1e3) / 1e9 / hbm_peak) if traffic else None,
+                "tensor_pipe_active_pct": measured(name, tag)[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": avg_ms, "launches_timed": table[key][0],
                 "share_of_library_kernel_time": table[key][1] / tot_ms,
                 "timing": "CUDA events around each launch, 3 eager steps after the timed region"}
@@ -558,7 +570,8 @@ def run_ours(args):
                 "algorithmic_tflops": 2 * macs * n / (avg_ms / 1e3) / 1e12,
                 "executed_over_algorithmic": 3, "hbm_gbs": nbytes / (avg_ms / 1e3) / 1e9, "hbm_frac": nbytes / (avg_ms / 1e3) / 1e9 / hbm_peak,
                 "algorithmic_bytes_per_launch": nbytes, "avg_launch_ms": avg_ms, "launches_timed": table[key][0],
-                "share_of_library_kernel_time": table[key][1] / tot_ms, "traffic": None}
+                "share_of_library_kernel_time": table[key][1] / tot_ms, "traffic": measured(name, key[1])[0],
+                "tensor_pipe_active_pct_ncu": measured(name, key[1])[1]}
 
     roof = roofline_of(dom)                                  # the kernel with the largest share of the step
     roof_grid = roofline_of(grid_dom) if grid_dom is not None else None   # the hash-grid gather (north star)

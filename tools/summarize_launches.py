@@ -8,6 +8,9 @@ import re
 import sys
 
 
+OURS = ("emer::", "tc::", "tcw::", "ff::", "wmn::")
+
+
 def main():
     path, title = sys.argv[1], sys.argv[2]
     with open(path) as f:
@@ -19,15 +22,16 @@ def main():
         if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
         name = re.sub(r"^void ", "", r["Kernel Name"])
-        name = re.sub(r"\(.*$", "", name) if name.startswith(("emer::", "tc::", "tcw::")) else name
         name = name.replace("at::", "").replace("emer::tc::", "tc::").replace("emer::tcw::", "tcw::")
+        name = name.replace("emer::ff::", "ff::").replace("emer::wmn::", "wmn::")
+        name = re.sub(r"\(.*$", "", name) if name.startswith(OURS) else name
         ns = float(r["Metric Value"].replace(",", ""))
         if r.get("Metric Unit", "ns") in ("us", "usecond"):
             ns *= 1000.0
         total[name] = total.get(name, 0.0) + ns
         count[name] += 1
     all_ns = sum(total.values())
-    ours = sum(v for k, v in total.items() if k.startswith(("emer::", "tc::", "tcw::")))
+    ours = sum(v for k, v in total.items() if k.startswith(OURS))
     print(f"# {title}\n")
     print("`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES, "
           "not absolutes).")
