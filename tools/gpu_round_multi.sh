@@ -1,5 +1,6 @@
 #!/bin/bash
-# Multi-GPU visit (gpurun --gpus N): NCCL test of the data-parallel step, bench in both exchange modes and the torch arm.
+# Multi-GPU visit (gpurun --gpus N): NCCL test of the data-parallel step (N = 2), bench in both exchange modes, the torch arm,
+# and (N = 8) the strong-scaling flow configuration of BASELINE.json configs[3].
 set -u
 mkdir -p gpurun_out
 N=${1:-2}; tag=${2:-m}
@@ -9,13 +10,13 @@ if [ "$N" = "2" ]; then
 fi
 for mode in sharded allreduce; do
   timeout 600 bash -c "$(declare -f run); N=$N run 295$((RANDOM % 90 + 10)) --dp-mode $mode" > gpurun_out/bench_n${N}_${mode}_$tag.log 2> gpurun_out/bench_n${N}_${mode}_$tag.err
-  echo "$mode: $(head -c 260 gpurun_out/bench_n${N}_${mode}_$tag.log)"; tail -3 gpurun_out/bench_n${N}_${mode}_$tag.err | cut -c1-200
+  echo "$mode: $(tail -1 gpurun_out/bench_n${N}_${mode}_$tag.log | head -c 230)"
 done
 timeout 600 bash -c "$(declare -f run); N=$N run 296$((RANDOM % 90 + 10)) --optimizer torch" > gpurun_out/bench_n${N}_torch_$tag.log 2> gpurun_out/bench_n${N}_torch_$tag.err
-echo "torch arm: $(head -c 260 gpurun_out/bench_n${N}_torch_$tag.log)"
-timeout 600 bash -c "$(declare -f run); N=$N run 297$((RANDOM % 90 + 10)) --dp-mode sharded --no-defer-gather" > gpurun_out/bench_n${N}_nodefer_$tag.log 2> gpurun_out/bench_n${N}_nodefer_$tag.err
-echo "sharded, gather not deferred: $(head -c 260 gpurun_out/bench_n${N}_nodefer_$tag.log)"
+echo "torch arm: $(tail -1 gpurun_out/bench_n${N}_torch_$tag.log | head -c 230)"
 if [ "$N" = "8" ]; then
   timeout 600 bash -c "$(declare -f run); N=$N run 298$((RANDOM % 90 + 10)) --scaling strong --rays 16384 --variant flow" > gpurun_out/bench_n${N}_strong_flow_$tag.log 2> gpurun_out/bench_n${N}_strong_flow_$tag.err
-  echo "strong flow 16384: $(head -c 300 gpurun_out/bench_n${N}_strong_flow_$tag.log)"
+  echo "strong flow 16384: $(tail -1 gpurun_out/bench_n${N}_strong_flow_$tag.log | head -c 300)"; tail -3 gpurun_out/bench_n${N}_strong_flow_$tag.err | cut -c1-200
+  timeout 600 bash -c "$(declare -f run); N=$N run 299$((RANDOM % 90 + 10)) --scaling strong --rays 8192 --variant flow_feat" > gpurun_out/bench_n${N}_strong_flowfeat_$tag.log 2> gpurun_out/bench_n${N}_strong_flowfeat_$tag.err
+  echo "strong flow_feat 8192: $(tail -1 gpurun_out/bench_n${N}_strong_flowfeat_$tag.log | head -c 300)"
 fi
