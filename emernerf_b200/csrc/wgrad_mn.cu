@@ -26,7 +26,6 @@ namespace wmn {
 
 using namespace emer::tc;
 
-constexpr int TILE = 64;                 // rows per pipeline stage (8 k-steps of 8 rows)
 constexpr int NCONV = 256;               // converter threads
 constexpr int NTHREADS = NCONV + 32;     // + the MMA-issuing warp
 constexpr int NOUT = 64;
@@ -58,7 +57,12 @@ struct Params {
     int64_t n;
 };
 
-template <int KXP, int LAYOUT, int STAGES>
+// TILE rows per pipeline stage (TILE / 8 k-steps of 8 rows).  Per tile a converter thread: waits for its own cp.async
+// pieces, splits them, arrives on full[stage] -- and only THEN waits for the MMAs of the previous tile to retire and
+// refills that tile's stage, so the split of tile t runs while the tensor pipe works on tile t - 1 (the first version
+// waited for the MMAs before splitting: split and MMA alternated, 110 us for 268 MB, profiles/r2_chain_ncu_summary.md).
+// Loads run STAGES - 1 tiles ahead of the split.
+template <int KXP, int LAYOUT, int STAGES, int TILE>
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_mn_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int MBA = KXP / 32, MBB = NOUT / 32;
@@ -94,13 +98,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_mn_kernel(const Params p) {
     if (is_issuer) {
         const uint32_t idesc = make_idesc(128, NOUT) | (1u << 15) | (1u << 16);       // A and B MN-major
         const uint32_t sbase = smem_u32(smem);
-        uint32_t ph[STAGES];
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) ph[s] = 0;
+        int s = 0;
+        uint32_t par = 0;                          // stage and parity of tile t: t % STAGES, (t / STAGES) & 1
         for (int t = 0; t < my_tiles; ++t) {
-            const int s = t % STAGES;
-            mbar_wait(&full_bar[s], ph[s]);
-            ph[s] ^= 1u;
+            mbar_wait(&full_bar[s], par);
             tc_fence_after();
             if (mma_issue_lane(tid)) {
                 const uint32_t a_hi = sbase + s * STAGE_BYTES, a_lo = a_hi + A_BYTES, b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
@@ -116,77 +117,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_mn_kernel(const Params p) {
                 tc_commit(&empty_bar[s]);
             }
             __syncwarp();
+            if (++s == STAGES) { s = 0; par ^= 1u; }
         }
     } else {
         constexpr int XQ = KXP / 4, ZQ = NOUT / 4;                   // 16-byte pieces per row
         constexpr int XP = TILE * XQ / NCONV, ZP = TILE * ZQ / NCONV; // pieces per thread per tile
-        const int kq = (p.k + 3) / 4;
-        auto issue = [&](int t) {
-            const int s = t % STAGES;
+        constexpr int XR = NCONV / XQ, ZR = NCONV / ZQ;               // rows between two pieces of one thread
+        static_assert(XP >= 1 && ZP >= 1 && XR % ATOM_ROWS == 0 && ZR % ATOM_ROWS == 0, "tile too small for 256 converters");
+        // a thread's pieces sit in one column of 16 bytes, XR (ZR) rows apart: whole swizzle atoms apart, so their
+        // shared-memory offsets differ by a constant
+        constexpr int XSTEP = (XR / ATOM_ROWS) * A_SBO, ZSTEP = (ZR / ATOM_ROWS) * B_SBO;
+        const int xr0 = tid / XQ, xc = tid % XQ, zr0 = tid / ZQ, zc = tid % ZQ;
+        const int xoff0 = piece_off<LAYOUT>(xc, xr0, MBA), zoff0 = piece_off<LAYOUT>(zc, zr0, MBB);
+        const bool x_col_ok = xc < (p.k + 3) / 4;
+        const float* xsrc = p.x + xc * 4;
+        const float* zsrc = p.dz + zc * 4;
+        auto issue = [&](int t, int s) {
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE;
-            uint8_t* a_hi = smem + s * STAGE_BYTES;
-            uint8_t* b_hi = a_hi + 2 * A_BYTES;
+            uint8_t* a_hi = smem + s * STAGE_BYTES + xoff0;
+            uint8_t* b_hi = smem + s * STAGE_BYTES + 2 * A_BYTES + zoff0;
 #pragma unroll
             for (int i = 0; i < XP; ++i) {
-                const int e = tid + i * NCONV, r = e / XQ, c = e % XQ;
-                const int64_t row = row0 + r;
-                const bool ok = row < p.n && c < kq;
-                cp_async16(a_hi + piece_off<LAYOUT>(c, r, MBA), ok ? p.x + row * p.ldx + c * 4 : p.x, ok ? 16u : 0u);
+                const int64_t row = row0 + xr0 + i * XR;
+                const bool ok = x_col_ok && row < p.n;
+                cp_async16(a_hi + i * XSTEP, ok ? xsrc + row * p.ldx : p.x, ok ? 16u : 0u);
             }
 #pragma unroll
             for (int i = 0; i < ZP; ++i) {
-                const int e = tid + i * NCONV, r = e / ZQ, c = e % ZQ;
-                const int64_t row = row0 + r;
+                const int64_t row = row0 + zr0 + i * ZR;
                 const bool ok = row < p.n;
-                cp_async16(b_hi + piece_off<LAYOUT>(c, r, MBB), ok ? p.dz + row * p.lddz + c * 4 : p.dz, ok ? 16u : 0u);
+                cp_async16(b_hi + i * ZSTEP, ok ? zsrc + row * p.lddz : p.dz, ok ? 16u : 0u);
             }
         };
+#pragma unroll
         for (int t = 0; t < STAGES - 1; ++t) {
-            if (t < my_tiles) issue(t);
+            if (t < my_tiles) issue(t, t);
             cp_async_commit();
         }
         float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t eph[STAGES];
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) eph[s] = 0;
+        int s = 0, sn = STAGES - 1;                  // stages of tile t and of tile t + STAGES - 1
+        uint32_t epar = 1;                           // parity of the empty-barrier phase tile t + STAGES - 1 waits for:
+                                                     // use (tn / STAGES) - 1 of its stage, first needed at tn = STAGES
         for (int t = 0; t < my_tiles; ++t) {
-            // prefetch tile t + STAGES - 1 into the stage tile t - 1 used: its MMAs must have retired
-            const int tn = t + STAGES - 1;
-            if (tn < my_tiles) {
-                const int sn = tn % STAGES;
-                if (tn >= STAGES) { mbar_wait(&empty_bar[sn], eph[sn]); eph[sn] ^= 1u; }
-                issue(tn);
-            }
-            cp_async_commit();
-            cp_async_wait<STAGES - 1>();                     // this thread's pieces of tile t have landed
-            const int s = t % STAGES;
-            uint8_t* a_hi = smem + s * STAGE_BYTES;
-            uint8_t* a_lo = a_hi + A_BYTES;
-            uint8_t* b_hi = a_lo + A_BYTES;
-            uint8_t* b_lo = b_hi + B_BYTES;
+            cp_async_wait<STAGES - 2>();                     // this thread's pieces of tile t have landed
+            uint8_t* a_hi = smem + s * STAGE_BYTES + xoff0;
+            uint8_t* b_hi = smem + s * STAGE_BYTES + 2 * A_BYTES + zoff0;
 #pragma unroll
             for (int i = 0; i < XP; ++i) {
-                const int e = tid + i * NCONV, r = e / XQ, c = e % XQ;
-                const int off = piece_off<LAYOUT>(c, r, MBA);
-                const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+                float4* ph = reinterpret_cast<float4*>(a_hi + i * XSTEP);
+                const float4 v = *ph;
                 float4 h, l;
                 split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
-                *reinterpret_cast<float4*>(a_hi + off) = h;
-                *reinterpret_cast<float4*>(a_lo + off) = l;
+                *ph = h;
+                *reinterpret_cast<float4*>(a_hi + i * XSTEP + A_BYTES) = l;
             }
 #pragma unroll
             for (int i = 0; i < ZP; ++i) {
-                const int e = tid + i * NCONV, r = e / ZQ, c = e % ZQ;
-                const int off = piece_off<LAYOUT>(c, r, MBB);
-                const float4 v = *reinterpret_cast<const float4*>(b_hi + off);
-                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;     // (c == tid % 16 for every i)
+                float4* ph = reinterpret_cast<float4*>(b_hi + i * ZSTEP);
+                const float4 v = *ph;
+                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;     // (column zc for every i)
                 float4 h, l;
                 split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
-                *reinterpret_cast<float4*>(b_hi + off) = h;
-                *reinterpret_cast<float4*>(b_lo + off) = l;
+                *ph = h;
+                *reinterpret_cast<float4*>(b_hi + i * ZSTEP + B_BYTES) = l;
             }
             fence_async_proxy();
             mbar_arrive(&full_bar[s]);
+            // refill the stage tile t - 1 used with tile t + STAGES - 1: the MMAs of t - 1 had this tile's split to retire
+            const int tn = t + STAGES - 1;
+            if (tn < my_tiles) {
+                if (tn >= STAGES) mbar_wait(&empty_bar[sn], epar);
+                issue(tn, sn);
+            }
+            cp_async_commit();
+            if (++s == STAGES) s = 0;
+            if (++sn == STAGES) { sn = 0; epar ^= 1u; }
         }
         cp_async_wait<0>();
         // ---- flush: wait for the last tile's MMAs, then lane f of the accumulator holds dW^T[f, 0..63]
@@ -241,6 +246,7 @@ extern "C" int emer_linear_tc_bwd_weight_mn(const float* x, int64_t ldx, const f
     EMER_REQUIRE(ldx % 4 == 0 && lddz % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dz & 15) == 0 && (k + 3) / 4 * 4 <= ldx,
                  "emer_linear_tc_bwd_weight_mn: rows must be 16-byte aligned");
     Params p{x, ldx, k, dz, lddz, dw, db, n};
+    constexpr int TILE = 32;
     const int64_t n_tiles = ceil_div(n, TILE);
     int64_t grid = sm_count();
     if (grid > n_tiles) grid = n_tiles;
@@ -260,8 +266,9 @@ extern "C" int emer_linear_tc_bwd_weight_mn(const float* x, int64_t ldx, const f
     const int dev = current_device();
     constexpr int LAYOUT = EMER_MN_LAYOUT;
     int rc;
-    if (k <= 64) rc = launch(wgrad_mn_kernel<64, LAYOUT, 3>, 3 * (4 * TILE * 64 * 4) + 4096 + 1024, configured_dev[0][dev]);
-    else rc = launch(wgrad_mn_kernel<128, LAYOUT, 2>, 2 * (2 * TILE * 128 * 4 + 2 * TILE * 64 * 4) + 4096 + 1024, configured_dev[1][dev]);
+    // 192 KB of stages either way: 6 x 32 KB (k <= 64) or 4 x 48 KB, + barriers and the bias scratch
+    if (k <= 64) rc = launch(wgrad_mn_kernel<64, LAYOUT, 6, TILE>, 6 * (4 * TILE * 64 * 4) + 4096 + 1024, configured_dev[0][dev]);
+    else rc = launch(wgrad_mn_kernel<128, LAYOUT, 4, TILE>, 4 * (2 * TILE * 128 * 4 + 2 * TILE * 64 * 4) + 4096 + 1024, configured_dev[1][dev]);
     if (rc) return rc;
     return check_launch("emer_linear_tc_bwd_weight_mn");
 }
