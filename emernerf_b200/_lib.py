@@ -37,7 +37,9 @@ _SIGNATURES = {
     "emer_linear_tc_bwd_weight_mn": [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, _P],
     "emer_pdf_resample": [_P, _P, c_int, c_int, _P, c_float, c_float, c_int, _P, _P, _P, c_int64, _P],
     "emer_prop_level": [POINTER(EmerGridDesc), _P, _P, c_int, c_int, _P, c_float, c_float, c_int, _P, _P, _P, c_int, _P,
-                        _P, _P, _P, _P, _P, _P, _P, c_int64, _P],
+                        _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P],
+    "emer_prop_level_bwd": [POINTER(EmerGridDesc), _P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
+                            _P, _P, c_int64, _P],
     "emer_field_tail_fwd": [_P, c_int64, c_int, _P, _P, _P, c_int, _P, c_int64, _P, c_int64, c_int, _P],
     "emer_field_tail_bwd": [_P, c_int64, _P, c_int64, c_int, _P, _P, _P, c_int, c_int64, c_int, _P],
     "emer_field_fwd": [_P, c_int64, c_int, _P, _P, _P, _P, c_int, _P, c_int64, _P, _P, c_int64, _P, _P, _P, c_int, _P, _P, _P,

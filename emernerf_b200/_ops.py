@@ -107,6 +107,9 @@ def _grad_sink(t: Optional[Tensor]):
 # gradients, which no weight gradient feeds; the optimizer (or the reduction of the MLP gradients) joins the side stream
 # first (:func:`join_side_streams`).  Captured into the step's CUDA graph this becomes two parallel branches.
 WGRAD_STREAM = os.environ.get("EMER_WGRAD_STREAM", "1") == "1"
+# proposal levels on the steps that update the proposal networks: "fused" = emer_prop_level + emer_prop_level_bwd,
+# "layers" = the modular autograd path (contract, grid, two layers, trunc_exp, composite)
+PROP_TRAIN = os.environ.get("EMER_PROP_TRAIN", "fused")
 _SIDE: Dict[int, "torch.cuda.Stream"] = {}
 _PENDING: Dict[int, bool] = {}
 _AFTER_JOIN: list = []          # small updates of buffers the main stream also writes: run there, after the join
@@ -893,8 +896,9 @@ def pdf_resample(vals: Tensor, cdfs: Tensor, n: int, bias: Optional[Tensor], s_m
 @torch.no_grad()
 def prop_level(prev_s: Tensor, prev_cdf: Tensor, n: int, bias: Optional[Tensor], s_min: float, s_max: float, kind: str,
                origins: Tensor, dirs: Tensor, aabb: Tensor, unbounded: bool, desc: GridDesc, table: Tensor,
-               w0: Tensor, b0: Tensor, w1: Tensor, b1: Tensor):
-    """One proposal level in one launch (no autograd): returns (s_edges, t_edges, cdf), each [R, n+1]."""
+               w0: Tensor, b0: Tensor, w1: Tensor, b1: Tensor, want_sigma: bool = False):
+    """One proposal level in one launch (no autograd): returns (s_edges, t_edges, cdf), each [R, n+1] -- and, with
+    ``want_sigma``, the level's densities [R, n] (what ``emer_prop_level_bwd`` starts from)."""
     _need_cuda(prev_s, prev_cdf, origins, dirs, table)
     prev_s, prev_cdf = _f32c(prev_s), _f32c(prev_cdf)
     r, m1 = prev_cdf.shape
@@ -902,6 +906,7 @@ def prop_level(prev_s: Tensor, prev_cdf: Tensor, n: int, bias: Optional[Tensor],
     out_s = torch.empty((r, n + 1), dtype=torch.float32, device=dev)
     out_t = torch.empty_like(out_s)
     out_cdf = torch.empty_like(out_s)
+    sigma = torch.empty((r, n), dtype=torch.float32, device=dev) if want_sigma else None
     if bias is not None:
         bias = _f32c(bias.reshape(-1))
     # every converted tensor is bound to a local that outlives the launch: a temporary copy made by _f32c would be
@@ -912,8 +917,81 @@ def prop_level(prev_s: Tensor, prev_cdf: Tensor, n: int, bias: Optional[Tensor],
         raise ValueError(f"prop_level: origins / dirs must be [{r}, 3], got {tuple(o.shape)} / {tuple(d.shape)}")
     _lib.call("emer_prop_level", ctypes.byref(desc.c), _ptr(prev_s), _ptr(prev_cdf), m1, n, _ptr(bias), float(s_min),
               float(s_max), STOT_KINDS[kind], _ptr(o), _ptr(d), _ptr(box), int(unbounded), _ptr(tab), _ptr(w0c),
-              _ptr(b0c), _ptr(w1c), _ptr(b1c), _ptr(out_s), _ptr(out_t), _ptr(out_cdf), r, _stream())
+              _ptr(b0c), _ptr(w1c), _ptr(b1c), _ptr(out_s), _ptr(out_t), _ptr(out_cdf), _ptr(sigma), r, _stream())
+    if want_sigma:
+        return out_s, out_t, out_cdf, sigma
     return out_s, out_t, out_cdf
+
+
+class _PropLevelTrain(torch.autograd.Function):
+    """A proposal level on the steps that update the proposal networks: the same single launch as the no-grad steps
+    forward (so both kinds of step draw bit-identical samples), and a backward that is one launch for the MLP
+    (``emer_prop_level_bwd``: recomputes the grid features and hidden units instead of saving [N, 64] activations) plus
+    the grid scatter.  Only ``cdf`` carries gradient (the sample positions are drawn without,
+    third_party/nerfacc_prop_net.py:147-170 of the reference)."""
+
+    @staticmethod
+    def forward(ctx, table, w0, b0, w1, b1, prev_s, prev_cdf, n, bias, s_min, s_max, kind, origins, dirs, aabb,
+                unbounded, desc):
+        out_s, out_t, out_cdf, sigma = prop_level(prev_s, prev_cdf, n, bias, s_min, s_max, kind, origins, dirs, aabb,
+                                                  unbounded, desc, table, w0, b0, w1, b1, want_sigma=True)
+        ctx.save_for_backward(table, w0, b0, w1, b1, out_t, sigma, origins, dirs, aabb)
+        ctx.desc, ctx.unbounded, ctx.n = desc, bool(unbounded), n
+        ctx.sinks = [_grad_sink(t) for t in (table, w0, b0, w1, b1)]
+        ctx.mark_non_differentiable(out_s, out_t)
+        return out_s, out_t, out_cdf
+
+    @staticmethod
+    def backward(ctx, _ds, _dt, d_cdf):
+        table, w0, b0, w1, b1, t_edges, sigma, origins, dirs, aabb = ctx.saved_tensors
+        desc, n = ctx.desc, ctx.n
+        r = t_edges.shape[0]
+        dev = t_edges.device
+        none = (None,) * 12
+        if d_cdf is None:
+            return (None,) * 5 + none
+        _need_cuda(d_cdf, table)
+        d_cdf = _f32c(d_cdf)
+        lf = desc.n_output_dims
+        xc = torch.empty((r * n, 3), dtype=torch.float32, device=dev)
+        d_enc = torch.empty((r * n, lf), dtype=torch.float32, device=dev)
+        outs = []
+        for t, sink in zip((table, w0, b0, w1, b1), ctx.sinks):
+            if sink is not None:
+                outs.append(sink[0])
+            else:
+                outs.append(torch.zeros(t.shape, dtype=torch.float32, device=dev))
+        d_table, d_w0, d_b0, d_w1, d_b1 = outs
+        tsink = ctx.sinks[0]
+        if tsink is not None and tsink[2] is not None and not tsink[2]():
+            d_table.zero_()                    # L2 write-allocate before the scatter (see _GridEncode.backward)
+        o, d, box = _f32c(origins), _f32c(dirs), _f32c(aabb.reshape(-1))
+        tab, w0c, b0c, w1c = _f32c(table), _f32c(w0), _f32c(b0), _f32c(w1.reshape(-1))
+        _lib.call("emer_prop_level_bwd", ctypes.byref(desc.c), _ptr(t_edges), _ptr(sigma), _ptr(d_cdf), n, _ptr(o), _ptr(d),
+                  _ptr(box), int(ctx.unbounded), _ptr(tab), _ptr(w0c), _ptr(b0c), _ptr(w1c), _ptr(xc), _ptr(d_enc),
+                  _ptr(d_w0), _ptr(d_b0), _ptr(d_w1), _ptr(d_b1), r, _stream())
+        _lib.call("emer_grid_bwd", ctypes.byref(desc.c), _ptr(xc), _ptr(tab), _ptr(d_enc), _ptr(d_table), None, r * n,
+                  _stream())
+        grads = []
+        for g, sink in zip(outs, ctx.sinks):
+            if sink is not None:
+                sink[1]()
+                grads.append(None)
+            else:
+                grads.append(g)
+        return tuple(grads) + none
+
+
+def prop_level_train_usable(desc: GridDesc) -> bool:
+    return PROP_TRAIN == "fused" and desc.n_dims == 3 and desc.n_feat == 1 and desc.n_output_dims in (4, 8)
+
+
+def prop_level_train(prev_s: Tensor, prev_cdf: Tensor, n: int, bias: Optional[Tensor], s_min: float, s_max: float,
+                     kind: str, origins: Tensor, dirs: Tensor, aabb: Tensor, unbounded: bool, desc: GridDesc,
+                     table: Tensor, w0: Tensor, b0: Tensor, w1: Tensor, b1: Tensor):
+    """(s_edges, t_edges, cdf) of one proposal level, ``cdf`` differentiable w.r.t. the table and the MLP."""
+    return _PropLevelTrain.apply(table, w0, b0, w1, b1, prev_s, prev_cdf, n, bias, s_min, s_max, kind, origins, dirs,
+                                 aabb, unbounded, desc)
 
 
 # ----------------------------------------------------------------------------- volume rendering

@@ -136,12 +136,26 @@ int emer_pdf_resample(const float* vals, const float* cdfs, int m1, int n, const
  * third_party/nerfacc_prop_net.py:147-170 + render_utils.py:314-324 + radiance_field.py:825-841):
  * resample n intervals from (prev_s, prev_cdf)[R, m1], s->t warp, march, contraction + selector, 3-D hash
  * grid, Linear(LF,64)-ReLU-Linear(64,1), trunc_exp(x-1), transmittance scan -> out_cdf[R, n+1].
- * out_s / out_t [R, n+1] are bit-identical to emer_pdf_resample's. */
+ * out_s / out_t [R, n+1] are bit-identical to emer_pdf_resample's.  out_sigma [R, n] (may be NULL) keeps the level's
+ * densities for emer_prop_level_bwd. */
 int emer_prop_level(const emer_grid_desc* g, const float* prev_s, const float* prev_cdf, int m1, int n,
                     const float* bias, float s_min, float s_max, int stot_kind, const float* origins,
                     const float* dirs, const float* aabb6, int unbounded, const float* table,
                     const float* w0, const float* b0, const float* w1, const float* b1, float* out_s,
-                    float* out_t, float* out_cdf, int64_t n_rays, void* stream);
+                    float* out_t, float* out_cdf, float* out_sigma, int64_t n_rays, void* stream);
+
+/* Backward of one proposal level on the steps that update the proposal networks (the autograd graph the reference
+ * builds through third_party/nerfacc_prop_net.py:161-170 -> render_utils.py:314-324 -> radiance_field.py:825-841 ->
+ * nerfacc render_transmittance_from_density): the interlevel loss reaches the level only through d_cdf [R, n+1].
+ * t_edges [R, n+1] and sigma [R, n] are the forward's out_t / out_sigma.  Recomputes positions, grid features and
+ * hidden units; ACCUMULATES d_w0 [64, LF], d_b0 [64], d_w1 [64], d_b1 [1]; WRITES xc [R n, 3] (grid coordinates) and
+ * d_enc [R n, LF], which emer_grid_bwd(g, xc, table, d_enc, d_table, NULL, R n) scatters into the table gradient.
+ * Grids of 4 or 8 levels x 1 feature (the shipped proposal grids). */
+int emer_prop_level_bwd(const emer_grid_desc* g, const float* t_edges, const float* sigma, const float* d_cdf, int n,
+                        const float* origins, const float* dirs, const float* aabb6, int unbounded,
+                        const float* table, const float* w0, const float* b0, const float* w1, float* xc,
+                        float* d_enc, float* d_w0, float* d_b0, float* d_w1, float* d_b1, int64_t n_rays,
+                        void* stream);
 
 /* ---- field tail: between the base MLP and the colour head (radiance_field.py:417-422,622-647) ---
  * forward : out[n, 0:W4] = [feats[n, 0:G] | sinenc((dir[ray]+1)/2) (33) | emb[idx[ray]] (E) | 0-pad], W4 = G+33+E

@@ -307,7 +307,7 @@ def emer_pdf_resample(vals, cdfs, m1, n, bias, s_min, s_max, kind, out_s, out_t,
 
 
 def emer_prop_level(desc, prev_s, prev_cdf, m1, n, bias, s_min, s_max, kind, origins, dirs, aabb6, unbounded, table,
-                    w0, b0, w1, b1, out_s, out_t, out_cdf, n_rays, stream):
+                    w0, b0, w1, b1, out_s, out_t, out_cdf, out_sigma, n_rays, stream):
     geom = _geom(desc)
     lf = geom.n_output_dims
     _check_grid(geom)
@@ -326,6 +326,46 @@ def emer_prop_level(desc, prev_s, prev_cdf, m1, n, bias, s_min, s_max, kind, ori
         _view(out_s, n_rays, n + 1).copy_(s)
         _view(out_t, n_rays, n + 1).copy_(t)
         _view(out_cdf, n_rays, n + 1).copy_(1.0 - torch.cat([trans, torch.zeros_like(trans[:, :1])], -1))
+        if _addr(out_sigma):
+            _view(out_sigma, n_rays, n).copy_(sigma)
+
+
+def emer_prop_level_bwd(desc, t_edges, sigma, d_cdf, n, origins, dirs, aabb6, unbounded, table, w0, b0, w1, xc, d_enc,
+                        d_w0, d_b0, d_w1, d_b1, n_rays, stream):
+    """Autograd through the restated forward of the level (from the grid features on; the scatter is emer_grid_bwd)."""
+    geom = _geom(desc)
+    lf = geom.n_output_dims
+    _check_grid(geom)
+    _require(geom.n_dims == 3 and geom.n_feat == 1 and lf in (4, 8), "emer_prop_level_bwd: 3-D grids of 4 or 8 levels x 1 feature")
+    _require(n >= 1 and n + 1 <= 257, f"emer_prop_level_bwd: n={n} out of range")
+    _require(_aligned16(d_enc), "emer_prop_level_bwd: d_enc must be 16-byte aligned")
+    t = _view(t_edges, n_rays, n + 1)
+    t0, t1 = t[:, :-1], t[:, 1:]
+    with torch.no_grad():
+        pos = _view(origins, n_rays, 3)[:, None, :] + _view(dirs, n_rays, 3)[:, None, :] * (t0 + t1)[..., None] / 2.0
+        x = hotpath.contract_points(pos.reshape(-1, 3), _vec(aabb6, 6), bool(unbounded))
+        enc0 = tcnn_ref.grid_forward(x, _vec(table, geom.n_params), geom)
+    enc = enc0.clone().requires_grad_()
+    W0 = _view(w0, 64, lf).clone().requires_grad_()
+    B0 = _vec(b0, 64).clone().requires_grad_()
+    W1 = _view(w1, 1, 64).clone().requires_grad_()
+    # Like the kernel, work from the SAVED densities: sigma = exp(raw - 1) has d sigma / d raw = exp(min(raw - 1, 15))
+    # = min(sigma, e^15) (nerf_utils.py:59-75), so b1's value is not needed -- only that raw depends on it.
+    B1 = torch.zeros(1, requires_grad=True)
+    with torch.enable_grad():
+        raw = (torch.relu(enc @ W0.t() + B0) @ W1.t() + B1)[:, 0].reshape(n_rays, n)
+        sg = _view(sigma, n_rays, n)
+        sig = sg + torch.clamp(sg, max=float(np.exp(np.float32(15.0)))) * (raw - raw.detach())
+        trans, _ = nf.render_transmittance_from_density(t0, t1, sig)
+        cdf = 1.0 - torch.cat([trans, torch.zeros_like(trans[:, :1])], -1)
+        g_enc, g_w0, g_b0, g_w1, g_b1 = torch.autograd.grad(cdf, (enc, W0, B0, W1, B1), _view(d_cdf, n_rays, n + 1))
+    with torch.no_grad():
+        _view(xc, n_rays * n, 3).copy_(x)
+        _view(d_enc, n_rays * n, lf).copy_(g_enc)
+        _view(d_w0, 64, lf).add_(g_w0)
+        _vec(d_b0, 64).add_(g_b0)
+        _vec(d_w1, 64).add_(g_w1.reshape(-1))
+        _vec(d_b1, 1).add_(g_b1)
 
 
 # ----------------------------------------------------------------------------- field tail

@@ -393,6 +393,61 @@ def test_fused_proposal_level_vs_oracle(stratified):
     assert torch.equal(s2, s_got) and torch.equal(t2, t_got) and torch.equal(cdf2, cdf_got)
 
 
+@pytest.mark.parametrize("n_levels,n,R", [(4, 32, 64), (8, 128, 96), (8, 64, 33), (8, 40, 2100)])
+def test_fused_proposal_level_backward_vs_oracle(n_levels, n, R):
+    """emer_prop_level_bwd (+ emer_grid_bwd for the scatter): gradient of a proposal level's CDF row w.r.t. the hash
+    table and the 8->64->1 MLP, against autograd through the oracle's DensityField + transmittance on CPU
+    (third_party/nerfacc_prop_net.py:161-170 -> render_utils.py:314-324 -> radiance_field.py:825-841 of the reference).
+    The forward of the training form is the no-grad kernel itself (bit-identical samples and CDF).  R = 2100 makes a
+    warp of the persistent kernel walk several rays (444 resident CTAs x 8 warps)."""
+    from emernerf_b200 import _ops
+    from emernerf_b200.radiance_fields import build_density_field
+    from oracle import adapters
+
+    torch.manual_seed(3)
+    net = build_density_field(n_input_dims=3, n_levels=n_levels, max_resolution=96 if n_levels == 4 else 512,
+                              log2_hashmap_size=12 if n_levels == 4 else 15, n_features_per_level=1, unbounded=True)
+    net.set_aabb([-20.0, -20.0, -5.0, 20.0, 20.0, 10.0])
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        net.xyz_encoder.tcnn_encoding.params.copy_(torch.randn(net.xyz_encoder.tcnn_encoding.params.shape, generator=gen) * 0.5)
+    origins = torch.randn(R, 3, generator=gen) * 2.0
+    dirs = torch.randn(R, 3, generator=gen)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    prev_s = torch.tensor([[0.0, 1.0]]).repeat(R, 1)
+    prev_cdf = prev_s.clone()
+    jit = torch.rand(R, 1, generator=gen)
+    up = torch.randn(R, n + 1, generator=gen)
+    s_min, s_max = hotpath.s_bounds("uniform_lindisp", 0.1, 1000.0)
+
+    # oracle, CPU autograd
+    iv, _ = nf.importance_sampling(nf.RayIntervals(prev_s), prev_cdf, n, True, jitter=jit)
+    t = hotpath._s_to_t("uniform_lindisp", iv.vals, 0.1, 1000.0)
+    pos = origins[:, None, :] + dirs[:, None, :] * (t[:, :-1] + t[:, 1:])[..., None] / 2.0
+    sd = adapters.cpu_state_dict(net, requires_grad=True)
+    sig = hotpath.density_field_forward(sd, adapters.spec_from_module(net), pos)["density"].squeeze(-1)
+    trans, _ = nf.render_transmittance_from_density(t[:, :-1], t[:, 1:], sig)
+    cdf_want = 1.0 - torch.cat([trans, torch.zeros_like(trans[:, :1])], -1)
+    names = [k for k, _ in net.named_parameters()]
+    want = dict(zip(names, torch.autograd.grad((cdf_want * up).sum(), [sd[k] for k in names])))
+
+    net = net.to(DEV)
+    lin = [m for m in net.base_mlp if isinstance(m, torch.nn.Linear)]
+    args = (prev_s.to(DEV), prev_cdf.to(DEV), n, jit.to(DEV), s_min, s_max, "uniform_lindisp", origins.to(DEV),
+            dirs.to(DEV), net.aabb, True, net.xyz_encoder.desc, net.xyz_encoder.tcnn_encoding.params, lin[0].weight,
+            lin[0].bias, lin[1].weight, lin[1].bias)
+    s0, t0, cdf0 = _ops.prop_level(*args)
+    s1, t1, cdf1 = _ops.prop_level_train(*args)
+    assert torch.equal(s0, s1) and torch.equal(t0, t1) and torch.equal(cdf0, cdf1)
+    assert cdf1.requires_grad and not s1.requires_grad and not t1.requires_grad
+    assert rel_err(cdf1, cdf_want) < 2e-5
+    (cdf1 * up.to(DEV)).sum().backward()
+    got = dict(net.named_parameters())
+    for k in names:
+        assert got[k].grad is not None, k
+        assert rel_err(got[k].grad, want[k]) < 2e-4, (k, rel_err(got[k].grad, want[k]))
+
+
 @pytest.mark.parametrize("with_emb,extra,front", [(True, 0, 0), (True, 64, 0), (False, 0, 0), (True, 0, 64),
                                                   (False, 64, 32)])
 def test_field_tail_forward_backward_vs_torch(with_emb, extra, front):

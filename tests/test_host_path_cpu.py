@@ -70,16 +70,18 @@ def test_host_path_matches_reference_outputs(emulated, case, mode):
     assert_close_dict(out, want, tol)
     hit = set(emulated.CALLS)
     assert {"emer_grid_fwd", "emer_pdf_resample", "emer_composite_fwd", "emer_contract_fwd"} <= hit
-    if mode != "train":
-        assert "emer_prop_level" in hit                  # no proposal gradients -> the fused level
-    else:
-        assert "emer_prop_level" not in hit
+    assert "emer_prop_level" in hit                      # the fused level, with or without proposal gradients
     if mode != "lidar":
         assert {"emer_field_tail_fwd", "emer_accumulate_fwd"} <= hit
 
 
+@pytest.mark.parametrize("prop_train", ["fused", "layers"])
 @pytest.mark.parametrize("case", list(cases.CASES))
-def test_host_path_gradients_and_proposal_loss(emulated, case):
+def test_host_path_gradients_and_proposal_loss(emulated, monkeypatch, case, prop_train):
+    """``prop_train``: the proposal levels of an update step as emer_prop_level + emer_prop_level_bwd (default) or
+    through the modular autograd path (contract, grid, layers, trunc_exp, composite)."""
+    from emernerf_b200 import _ops
+    monkeypatch.setattr(_ops, "PROP_TRAIN", prop_train)
     g, field, props, est = _build(case)
     out = _render(g, field, props, est, "train")
     ploss = est.compute_loss(out["extras"]["trans"], 1024.0)
@@ -87,6 +89,7 @@ def test_host_path_gradients_and_proposal_loss(emulated, case):
     assert abs(ploss.item() - want_ploss) <= 1e-3 * max(1.0, abs(want_ploss))
     pnames = [k for k, _ in props[1].named_parameters()]
     pgrads = torch.autograd.grad(ploss, [v for _, v in props[1].named_parameters()])
+    assert ("emer_prop_level_bwd" in emulated.CALLS) == (prop_train == "fused")
     want_p = g.tensors("train/grad/prop1")
     for k, gr in zip(pnames, pgrads):
         assert rel_err(gr, want_p[k]) < 5e-3, k
