@@ -112,7 +112,7 @@ __device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
 }
 
 template <int K_ENC>
-__global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p) {
+__global__ void __maxnreg__(120) field_fwd_kernel(const FwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Smem m = smem_map(K_ENC, p.n_feat);
     float* bias_s = reinterpret_cast<float*>(smem + m.bias);
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
     const bool is_issuer = warp == EPI_THREADS / 32;
 
     if (tid == 0) {
-        mbar_init(&a_full[0], TILE_THREADS);
-        mbar_init(&a_full[1], TILE_THREADS);
+        mbar_init(&a_full[0], arrivals(TILE_THREADS));
+        mbar_init(&a_full[1], arrivals(TILE_THREADS));
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
             load_enc(tile + pair_stride);        // next tile's row: in flight under this tile's five layers
 
             // ---- stage 1: Hb = relu(D + bb0)
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 2: feats = D + bb1; sigma = exp(feats[0] - 1); geo -> operand; semantic half -> HBM
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 3: H0 = relu(D[0,64) + ray_bias0)
             const float* rb = p.ray_bias + ray * 128;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 4: H1 = relu(D[64,128) + ray_bias1)
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 5: rgb = sigmoid(D[0,3) + b2)
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
@@ -503,7 +503,7 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane, i
 }
 
 template <int K_ENC>
-__global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p) {
+__global__ void __maxnreg__(120) field_bwd_kernel(const BwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int KPAD = (K_ENC + 15) / 16 * 16;
     const BSmem m = bsmem_map(K_ENC, p.n_feat);
@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
     const bool is_issuer = warp == EPI_THREADS / 32;
 
     if (tid == 0) {
-        mbar_init(&a_full[0], TILE_THREADS);
-        mbar_init(&a_full[1], TILE_THREADS);
+        mbar_init(&a_full[0], arrivals(TILE_THREADS));
+        mbar_init(&a_full[1], arrivals(TILE_THREADS));
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 0 result: dZ1 = dH1 * (h1 > 0)
             uint32_t mask = relu_mask32(p.h1 + rsafe * H + half * 32, row_ok);        // columns 32 half .. 32 half + 31
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 1 result: dZ0 = dH0 * (h0 > 0)   (dG stays in the accumulator's upper half)
             mask = relu_mask32(p.hg + rsafe * 128 + half * 32, row_ok);
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 2 result: dF = dG (+ d_geo); dF[0] += d_sigma * exp(min(x, 15)), exp(x) = sigma (nerf_utils.py:72-75)
             float ds = 0.0f;
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             if (p.n_feat > H) {
                 // ---- second operand piece of stage 3: the gradient of the semantic half
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
                 }
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&a_full[wg]);
+                mbar_arrive_warp(&a_full[wg]);
             }
 
             // ---- stage 3 result: dZb = dHb * (hb > 0)
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_full[wg]);
+            mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 4 result: d_enc
             mbar_wait(&d_full[wg], ph); ph ^= 1u;

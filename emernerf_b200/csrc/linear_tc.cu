@@ -837,7 +837,9 @@ extern "C" int emer_linear_tc_bwd_weight(const float* x, int64_t ldx, const floa
     }
     const int64_t n_tiles = emer::ceil_div(n, p.w_rows);
     int64_t grid = emer::sm_count();
-    if (grid > n_tiles) grid = n_tiles;
+    // every CTA ends with n_out x k atomics onto the same addresses: with few tiles (the per-ray products, 8192 rows)
+    // one tile per CTA makes the flush the whole cost (79 us for 49 -> 128 over 8192 rows), so give a CTA >= 4 tiles
+    if (grid > emer::ceil_div(n_tiles, (int64_t)4)) grid = emer::ceil_div(n_tiles, (int64_t)4);
     tc_wgrad_kernel<<<(unsigned)grid, WNT_ALL, smem, (cudaStream_t)stream>>>(p);
     return emer::check_launch("emer_linear_tc_bwd_weight");
 }

@@ -144,12 +144,21 @@ __device__ __forceinline__ void pl_encode(const emer_grid_desc& g, const float* 
     }
 }
 
+template <int LF>
+__device__ __forceinline__ void pl_load_row(const float* __restrict__ row16, float (&w)[LF]) {     // 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < LF; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(row16 + i);
+        w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+    }
+}
+
 // LF_T > 0: compile-time feature count with F = 1 (the shipped proposal grids: 8 levels x 1 feature);
 // LF_T == 0: generic run-time loops.
 template <int LF_T>
 __global__ void __launch_bounds__(PL_WARPS * 32) prop_level_kernel(const PropParams p) {
     __shared__ float t_edges[PL_WARPS][PL_MAX_EDGES + 3];
-    __shared__ float w0s[PL_HID * PL_MAX_IN];
+    __shared__ __align__(16) float w0s[PL_HID * PL_MAX_IN];
     __shared__ float b0s[PL_HID], w1s[PL_HID];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int LF = LF_T > 0 ? LF_T : p.g.n_levels * p.g.n_feat;
@@ -205,8 +214,16 @@ __global__ void __launch_bounds__(PL_WARPS * 32) prop_level_kernel(const PropPar
 #pragma unroll 4
             for (int j = 0; j < PL_HID; ++j) {
                 float h = b0s[j];
+                if constexpr (LF_T > 0 && LF_T % 4 == 0) {
+                    // one 16-byte shared-memory load per 4 weights (broadcast), same fma chain
+                    float wr[LF_T];
+                    pl_load_row<LF_T>(w0s + j * LF_T, wr);
 #pragma unroll
-                for (int i = 0; i < LF; ++i) h = fmaf(w0s[j * LF + i], enc[i], h);
+                    for (int i = 0; i < LF_T; ++i) h = fmaf(wr[i], enc[i], h);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < LF; ++i) h = fmaf(w0s[j * LF + i], enc[i], h);
+                }
                 h = h > 0.0f ? h : 0.0f;
                 raw = fmaf(w1s[j], h, raw);
             }
@@ -263,7 +280,7 @@ template <int LF>
 __global__ void __launch_bounds__(PL_WARPS * 32) prop_level_bwd_kernel(const PropBwdParams p) {
     __shared__ float t_edges[PL_WARPS][PL_MAX_EDGES + 3];
     __shared__ float d_raw_s[PL_WARPS][PL_MAX_EDGES + 3];
-    __shared__ float w0s[PL_HID * LF];
+    __shared__ __align__(16) float w0s[PL_HID * LF];
     __shared__ float b0s[PL_HID], w1s[PL_HID];
     __shared__ float red[PL_HID * LF + 2 * PL_HID + 1];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -329,11 +346,13 @@ __global__ void __launch_bounds__(PL_WARPS * 32) prop_level_bwd_kernel(const Pro
 #pragma unroll 4
                 for (int j = 0; j < PL_HID; ++j) {
                     float h = b0s[j];
+                    float wr[LF];
+                    pl_load_row<LF>(w0s + j * LF, wr);
 #pragma unroll
-                    for (int i = 0; i < LF; ++i) h = fmaf(w0s[j * LF + i], enc[i], h);
+                    for (int i = 0; i < LF; ++i) h = fmaf(wr[i], enc[i], h);
                     const float dh = h > 0.0f ? d_raw * w1s[j] : 0.0f;
 #pragma unroll
-                    for (int i = 0; i < LF; ++i) d_enc[i] = fmaf(dh, w0s[j * LF + i], d_enc[i]);
+                    for (int i = 0; i < LF; ++i) d_enc[i] = fmaf(dh, wr[i], d_enc[i]);
                 }
                 const int64_t pt = ray * n + k;
                 p.xc[pt * 3] = xc[0]; p.xc[pt * 3 + 1] = xc[1]; p.xc[pt * 3 + 2] = xc[2];

@@ -134,6 +134,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Arrival of a whole (converged) warp.  EMER_WARP_ARRIVE=1: the lanes synchronise and ONE lane arrives, so a barrier
+// fed by 256 threads sees 8 shared-memory atomics per phase instead of 256 serialised ones on one word (the hand-off
+// latency of every stage of the fused chain and of every tile of the weight-gradient kernel).  The barrier is then
+// initialised with arrivals(threads).  Every lane must have executed its own fences (fence.proxy.async /
+// tcgen05.fence::before_thread_sync) before the call; __syncwarp orders them before the elected lane's release.
+#ifndef EMER_WARP_ARRIVE
+#define EMER_WARP_ARRIVE 1
+#endif
+__host__ __device__ constexpr int arrivals(int threads) { return EMER_WARP_ARRIVE ? threads / 32 : threads; }
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+#if EMER_WARP_ARRIVE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+    mbar_arrive(bar);
+#endif
+}
+
 // ---- operand A from TENSOR MEMORY (the ".ts" form): D[tmem] (+)= A[tmem] * B[smem]^T.  A is [128 lanes x K columns]
 // of 32-bit tf32 containers: lane = row, column = k; 8 columns per instruction.
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_mn_kernel(const Params p) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool is_issuer = warp == NCONV / 32;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], NCONV); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], arrivals(NCONV)); mbar_init(&empty_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_mn_kernel(const Params p) {
                 *reinterpret_cast<float4*>(b_hi + i * ZSTEP + B_BYTES) = l;
             }
             fence_async_proxy();
-            mbar_arrive(&full_bar[s]);
+            mbar_arrive_warp(&full_bar[s]);
             // refill the stage tile t - 1 used with tile t + STAGES - 1: the MMAs of t - 1 had this tile's split to retire
             const int tn = t + STAGES - 1;
             if (tn < my_tiles) {

@@ -255,7 +255,7 @@ class RadianceField(nn.Module):
         dirs, idx, emb = tail
         v = self.direction_encoding((dirs + 1.0) / 2.0)
         if emb is not None:
-            v = torch.cat([v, emb[idx]], dim=-1)
+            v = torch.cat([v, _ops.gather_rows(emb, idx)], dim=-1)
         c = v.shape[-1]
         l0, l1, _ = self.rgb_head.layers
         h = l0.out_features

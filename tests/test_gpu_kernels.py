@@ -712,3 +712,30 @@ def test_weight_gradient_mn_major_operands(k, n, ldx, lddz):
     tol = 2e-5 if n < 200000 else 5e-5               # fp32 accumulation over 8192 tiles in TMEM + 148 partial sums
     assert rel_err(dw, want_w) < tol, rel_err(dw, want_w)
     assert rel_err(db, want_b) < tol, rel_err(db, want_b)
+
+
+@pytest.mark.parametrize("k,n_out,n,ldx,lddz", [(64, 3, 40000 + 13, 64, 3), (64, 3, 524288, 64, 4), (64, 1, 9000, 128, 4),
+                                                (40, 4, 777, 40, 4), (256, 2, 5000, 256, 2), (37, 3, 4000, 37, 3),
+                                                (64, 6, 3000, 64, 8), (64, 3, 5, 64, 3)])
+@pytest.mark.parametrize("bias", [True, False])
+def test_narrow_weight_gradient(k, n_out, n, ldx, lddz, bias):
+    """emer_linear_narrow_bwd_weight (heads with n_out <= 8: sigma, rgb, sky, shadow): dW [n_out, k] and db accumulate
+    dZ^T X / column sums of dZ over all rows, against fp64.  Covers the 16-byte-vector kernel (k % 4 == 0, n_out <= 4;
+    dZ rows padded to 4 floats or not) and the scalar one (odd k, n_out > 4), strided rows and a ragged row count."""
+    from emernerf_b200 import _lib, _ops
+
+    g = torch.Generator(device=DEV).manual_seed(k * 7 + n_out)
+    xb = torch.randn(n, ldx, device=DEV, generator=g)
+    zb = torch.randn(n, lddz, device=DEV, generator=g)
+    x, dz = xb[:, :k], zb[:, :n_out]
+    dw0, db0 = torch.randn(n_out, k, device=DEV, generator=g), torch.randn(n_out, device=DEV, generator=g)
+    dw, db = dw0.clone(), db0.clone()
+    _ops._need_cuda(x)
+    _lib.call("emer_linear_narrow_bwd_weight", _ops._ptr(xb), ldx, _ops._ptr(zb), lddz, _ops._ptr(dw),
+              _ops._ptr(db) if bias else None, n, k, n_out, _ops._stream())
+    want_w = dw0.double() + dz.double().T @ x.double()
+    assert rel_err(dw, want_w) < 2e-5, rel_err(dw, want_w)
+    if bias:
+        assert rel_err(db, db0.double() + dz.double().sum(0)) < 2e-5
+    else:
+        assert torch.equal(db, db0)
