@@ -27,7 +27,7 @@ LINEAR_IMPL = os.environ.get("EMER_LINEAR", "tc")
 LINEAR_WGRAD_IMPL = os.environ.get("EMER_LINEAR_WGRAD", "mn")      # "mn": MN-major operands (csrc/wgrad_mn.cu) where the shape
                                                                    # allows, else "tc" (transposing, linear_tc.cu); "simt"
 SKIP_BWD_IMPL = os.environ.get("EMER_SKIP_BWD", "stack")   # "stack": one stacked product; "add": two + add
-TC_MIN_ROWS = 1024          # tiny per-ray heads are launch-bound either way
+TC_MIN_ROWS = int(os.environ.get("EMER_TC_MIN_ROWS", "1024"))   # below: the FP32-FMA kernels (tiny per-ray heads are launch-bound either way)
 STOT_KINDS = {"uniform": 0, "lindisp": 1, "sqrt": 2, "log": 3, "uniform_lindisp": 4, "uniform_lindisp_0": 5}
 
 

@@ -112,7 +112,7 @@ __device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
 }
 
 template <int K_ENC>
-__global__ void __maxnreg__(120) field_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const Smem m = smem_map(K_ENC, p.n_feat);
     float* bias_s = reinterpret_cast<float*>(smem + m.bias);
@@ -503,7 +503,7 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane, i
 }
 
 template <int K_ENC>
-__global__ void __maxnreg__(120) field_bwd_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int KPAD = (K_ENC + 15) / 16 * 16;
     const BSmem m = bsmem_map(K_ENC, p.n_feat);
