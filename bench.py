@@ -117,7 +117,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, 0.0
 
     def start(self):
         try:
@@ -130,16 +130,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.monotonic()] + [c.strip() for c in line.split(",")])
+
+    def mark(self, wait_s: float = 10.0):
+        """Called right before the timed region: nvidia-smi needs up to a few seconds for its first sample on a fresh
+        box (a 0.3 s timed region used to end before it), so wait for one, then count only what comes after."""
+        t_end = time.monotonic() + wait_s
+        while self.proc is not None and not self.rows and time.monotonic() < t_end:
+            time.sleep(0.02)
+        self.t_mark = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if r[0] >= self.t_mark]
+        sm = sorted(int(float(r[1])) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) < 8:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -404,19 +413,20 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     _lib.load()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                       # before the warm-up: its first sample takes a while
     tr = Trainer(args, rank, world, device)
     for i in range(args.warmup):
         tr.step(i, False)
+    if rank == 0:
+        clocks.mark()
     sync()
 
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = _lib.LAUNCHES
     tr.replayed_launches = 0
     ms = timed(tr, args.steps, False, sync)
     launches = (_lib.LAUNCHES - launches0) + tr.replayed_launches
-    clk = clocks.stop() if rank == 0 else None
 
     e2e = None
     if not args.no_e2e:
@@ -426,6 +436,8 @@ def run_ours(args):
         e2e = {"value": tr.rays * world * args.steps / (ms_e2e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": tr.h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps}
+    # clocks / throttle reasons sampled every 50 ms over both timed regions (device-resident and end-to-end)
+    clk = clocks.stop() if rank == 0 else None
 
     # per-kernel device times: CUDA events around every library launch over 3 eager steps, same
     # process / inputs / clocks, right after the timed region (a replayed graph cannot be event-timed

@@ -40,6 +40,7 @@ _SIGNATURES = {
                         _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P],
     "emer_prop_level_bwd": [POINTER(EmerGridDesc), _P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P,
                             _P, _P, c_int64, _P],
+    "emer_interlevel_loss": [_P, _P, c_int, _P, _P, c_int, c_float, _P, _P, c_int64, _P],
     "emer_field_tail_fwd": [_P, c_int64, c_int, _P, _P, _P, c_int, _P, c_int64, _P, c_int64, c_int, _P],
     "emer_field_tail_bwd": [_P, c_int64, _P, c_int64, c_int, _P, _P, _P, c_int, c_int64, c_int, _P],
     "emer_field_fwd": [_P, c_int64, c_int, _P, _P, _P, _P, c_int, _P, c_int64, _P, _P, c_int64, _P, _P, _P, c_int, _P, _P, _P,

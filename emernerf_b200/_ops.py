@@ -994,6 +994,48 @@ def prop_level_train(prev_s: Tensor, prev_cdf: Tensor, n: int, bias: Optional[Te
                                  aabb, unbounded, desc)
 
 
+# ----------------------------------------------------------------------------- interlevel (proposal) loss
+INTERLEVEL = os.environ.get("EMER_INTERLEVEL", "fused")       # "torch": the op-by-op restatement in nerfacc_prop_net.py
+
+
+class _InterlevelLoss(torch.autograd.Function):
+    """mean_k max(dq_k - dP_k, 0)^2 / (dP_k + 1e-5) of one proposal level against the blurred final-level histogram
+    (third_party/nerfacc_prop_net.py:182-240 of the reference); differentiable w.r.t. the level's CDF only -- the
+    target is detached there too."""
+
+    @staticmethod
+    def forward(ctx, prop_cdf: Tensor, s: Tensor, cdf: Tensor, prop_s: Tensor, pulse_width: float):
+        _need_cuda(prop_cdf, s, cdf, prop_s)
+        pc, sc, cc, ps = _f32c(prop_cdf), _f32c(s), _f32c(cdf), _f32c(prop_s)
+        r, m = sc.shape
+        n1 = pc.shape[1]
+        total = torch.zeros(1, dtype=torch.float32, device=pc.device)
+        grad = torch.empty_like(pc) if ctx.needs_input_grad[0] else None
+        _lib.call("emer_interlevel_loss", _ptr(sc), _ptr(cc), m, _ptr(ps), _ptr(pc), n1, float(pulse_width), _ptr(total),
+                  _ptr(grad), r, _stream())
+        ctx.count = float(r * (n1 - 1))
+        if grad is not None:
+            ctx.save_for_backward(grad)
+        return (total / ctx.count).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * (g / ctx.count), None, None, None, None
+
+
+def interlevel_loss_usable(s: Tensor, prop_s: Tensor) -> bool:
+    return (INTERLEVEL == "fused" and on_device(s) and s.dim() == 2 and prop_s.dim() == 2 and 2 <= s.shape[1] <= 129
+            and 2 <= prop_s.shape[1] <= 257)
+
+
+def interlevel_loss(s: Tensor, cdf: Tensor, prop_s: Tensor, prop_cdf: Tensor, pulse_width: float) -> Tensor:
+    if cdf.shape != s.shape or prop_cdf.shape != prop_s.shape or prop_s.shape[0] != s.shape[0]:
+        raise ValueError(f"interlevel_loss: edges / cdf shapes {tuple(s.shape)} {tuple(cdf.shape)} "
+                         f"{tuple(prop_s.shape)} {tuple(prop_cdf.shape)}")
+    return _InterlevelLoss.apply(prop_cdf, s, cdf.detach(), prop_s, pulse_width)
+
+
 # ----------------------------------------------------------------------------- embedding rows
 class _GatherRows(torch.autograd.Function):
     """``table[idx]`` for a small table hit by many repeated indices (the appearance embedding: 8192 rays over a few

@@ -157,6 +157,16 @@ int emer_prop_level_bwd(const emer_grid_desc* g, const float* t_edges, const flo
                         float* d_enc, float* d_w0, float* d_b0, float* d_w1, float* d_b1, int64_t n_rays,
                         void* stream);
 
+/* ---- anti-aliased interlevel loss of one proposal level, value and gradient in one launch (replaces, per level,
+ *      the ~40 torch launches of PropNetEstimator.compute_loss, third_party/nerfacc_prop_net.py:182-240 with
+ *      blur_stepfun :22-34 and sorted_interp_quad :37-60, and autograd's backward of them) -------------------------
+ * s, cdf: [R, m] final-level edges (normalised) and CDF (a constant of the loss); prop_s, prop_cdf: [R, n1] of the
+ * level; pulse_width: the level's blur radius.  ACCUMULATES sum_{rays, k} max(dq_k - dP_k, 0)^2 / (dP_k + 1e-5) into
+ * loss_sum[0] (the reference's .mean() divides by R (n1 - 1)) and WRITES its gradient w.r.t. prop_cdf into
+ * d_prop_cdf [R, n1] (may be NULL).  m <= 129, n1 <= 257. */
+int emer_interlevel_loss(const float* s, const float* cdf, int m, const float* prop_s, const float* prop_cdf, int n1,
+                         float pulse_width, float* loss_sum, float* d_prop_cdf, int64_t n_rays, void* stream);
+
 /* ---- field tail: between the base MLP and the colour head (radiance_field.py:417-422,622-647) ---
  * forward : out[n, 0:W4] = [feats[n, 0:G] | sinenc((dir[ray]+1)/2) (33) | emb[idx[ray]] (E) | 0-pad], W4 = G+33+E
  *           rounded up to 4; ld_out (% 4 == 0, >= W4) is only the row stride, so the rows may sit inside a

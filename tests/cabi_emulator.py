@@ -368,6 +368,27 @@ def emer_prop_level_bwd(desc, t_edges, sigma, d_cdf, n, origins, dirs, aabb6, un
         _vec(d_b1, 1).add_(g_b1)
 
 
+def emer_interlevel_loss(s, cdf, m, prop_s, prop_cdf, n1, pulse_width, loss_sum, d_prop_cdf, n_rays, stream):
+    """One level's term of oracle.hotpath.proposal_loss (sum instead of mean) and autograd's gradient of it."""
+    _require(2 <= m <= 129 and 2 <= n1 <= 257, f"emer_interlevel_loss: {m} final edges / {n1} proposal edges out of range")
+    _require(pulse_width > 0, "emer_interlevel_loss: pulse width must be positive")
+    S, C, PS = _view(s, n_rays, m), _view(cdf, n_rays, m), _view(prop_s, n_rays, n1)
+    PC = _view(prop_cdf, n_rays, n1).clone().requires_grad_()
+    with torch.enable_grad():
+        w_n = (C[:, 1:] - C[:, :-1]) / (S[:, 1:] - S[:, :-1])
+        c, w = hotpath.blur_stepfun(S, w_n, pulse_width)
+        area = 0.5 * (w[:, 1:] + w[:, :-1]) * (c[:, 1:] - c[:, :-1])
+        cd = torch.cat([torch.zeros_like(area[:, :1]), torch.cumsum(area, -1)], -1)
+        wp = PC[:, 1:] - PC[:, :-1]
+        w_s = torch.diff(hotpath.sorted_interp_quad(PS, c, w, cd), dim=-1)
+        total = ((w_s - wp).clamp_min(0) ** 2 / (wp + 1e-5)).sum()
+        (g,) = torch.autograd.grad(total, PC)
+    with torch.no_grad():
+        _vec(loss_sum, 1).add_(total.detach())
+        if _addr(d_prop_cdf):
+            _view(d_prop_cdf, n_rays, n1).copy_(g)
+
+
 # ----------------------------------------------------------------------------- field tail
 FT_DIR = 33
 

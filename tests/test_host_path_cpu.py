@@ -78,10 +78,12 @@ def test_host_path_matches_reference_outputs(emulated, case, mode):
 @pytest.mark.parametrize("prop_train", ["fused", "layers"])
 @pytest.mark.parametrize("case", list(cases.CASES))
 def test_host_path_gradients_and_proposal_loss(emulated, monkeypatch, case, prop_train):
-    """``prop_train``: the proposal levels of an update step as emer_prop_level + emer_prop_level_bwd (default) or
-    through the modular autograd path (contract, grid, layers, trunc_exp, composite)."""
+    """``prop_train``: the proposal levels of an update step as emer_prop_level + emer_prop_level_bwd and the
+    interlevel loss as emer_interlevel_loss (default), or both through the modular autograd paths (contract, grid,
+    layers, trunc_exp, composite; blur_stepfun / sorted_interp_quad in torch)."""
     from emernerf_b200 import _ops
     monkeypatch.setattr(_ops, "PROP_TRAIN", prop_train)
+    monkeypatch.setattr(_ops, "INTERLEVEL", "fused" if prop_train == "fused" else "torch")
     g, field, props, est = _build(case)
     out = _render(g, field, props, est, "train")
     ploss = est.compute_loss(out["extras"]["trans"], 1024.0)
@@ -90,6 +92,7 @@ def test_host_path_gradients_and_proposal_loss(emulated, monkeypatch, case, prop
     pnames = [k for k, _ in props[1].named_parameters()]
     pgrads = torch.autograd.grad(ploss, [v for _, v in props[1].named_parameters()])
     assert ("emer_prop_level_bwd" in emulated.CALLS) == (prop_train == "fused")
+    assert ("emer_interlevel_loss" in emulated.CALLS) == (prop_train == "fused")
     want_p = g.tensors("train/grad/prop1")
     for k, gr in zip(pnames, pgrads):
         assert rel_err(gr, want_p[k]) < 5e-3, k
