@@ -470,15 +470,18 @@ def run_ours(args):
         from torch.profiler import ProfilerActivity, profile
 
         tr._profiling = True
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            tr.step(0, False)
-            torch.cuda.synchronize()
+        for prg in (False, True):               # one eager step of each kind (without / with proposal update)
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                tr._step_body(tr.dev[0], prg)
+                torch.cuda.synchronize()
+            rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:40]
+            tot = sum(e.device_time_total for e in prof.key_averages())
+            n_launch = sum(e.count for e in prof.key_averages())
+            print(f"# --- all kernels of one eager step (proposal update = {prg}): {tot / 1e3:.3f} ms device time, "
+                  f"{n_launch} launches", file=sys.stderr)
+            for e in rows:
+                print(f"#   {e.device_time_total / 1e3:8.3f} ms n={e.count:4d}  {e.key[:110]}", file=sys.stderr)
         tr._profiling = False
-        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:40]
-        tot = sum(e.device_time_total for e in prof.key_averages())
-        print(f"# --- all kernels of one eager step: {tot / 1e3:.3f} ms device time", file=sys.stderr)
-        for e in rows:
-            print(f"#   {e.device_time_total / 1e3:8.3f} ms n={e.count:4d}  {e.key[:110]}", file=sys.stderr)
 
     if rank != 0:
         if world > 1:                     # leave together with rank 0 (see the end of this function)
