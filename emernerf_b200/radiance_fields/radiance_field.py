@@ -461,13 +461,21 @@ class RadianceField(nn.Module):
         return results
 
     # ------------------------------------------------------------------ heads
+    def _embed(self, idx: Tensor) -> Tensor:
+        """``self.appearance_embedding(idx)``; on the device through the sort-free gather (``_ops.gather_rows``): the
+        backward of nn.Embedding radix-sorts the indices every step."""
+        w = self.appearance_embedding.weight
+        if not _ops.on_device(w):
+            return self.appearance_embedding(idx)
+        return _ops.gather_rows(w, idx).reshape(*idx.shape, w.shape[1])
+
     def _appearance(self, like: Tensor, data_dict) -> Optional[Tensor]:
         if not (self.enable_cam_embedding or self.enable_img_embedding):
             return None
         if "cam_idx" in data_dict and self.enable_cam_embedding:
-            return self.appearance_embedding(data_dict["cam_idx"])
+            return self._embed(data_dict["cam_idx"])
         if "img_idx" in data_dict and self.enable_img_embedding:
-            return self.appearance_embedding(data_dict["img_idx"])
+            return self._embed(data_dict["img_idx"])
         mean = self.appearance_embedding.weight.mean(dim=0)
         return torch.ones((*like.shape[:-1], self.appearance_embedding_dim), device=like.device) * mean
 
