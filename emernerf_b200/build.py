@@ -29,7 +29,7 @@ NVCC_FLAGS = [
 ]
 # compile-time experiment switches of the kernels (see the comment at each #ifndef in csrc/): passed through
 # from the environment so that an A/B build is one command; the default build defines none of them
-for _flag in ("EMER_TC_ELECT_ONE", "EMER_WARP_ARRIVE"):
+for _flag in ("EMER_TC_ELECT_ONE", "EMER_WARP_ARRIVE", "EMER_CHAIN_STAGE"):
     if os.environ.get(_flag):
         NVCC_FLAGS.append(f"-D{_flag}={os.environ[_flag]}")
 

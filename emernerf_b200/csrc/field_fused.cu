@@ -58,6 +58,7 @@ struct FwdParams {
     float *sigma, *rgb;                                           // [N], [N, 3]
     float *save_hb, *save_hg, *save_h1, *save_sem;                // training saves: [N,64], [N,128]=[h0|geo], [N,64], [N,64]
     int64_t n;
+    int stg_off;                                                  // byte offset of the staging tiles in shared memory, 0 = none
 };
 
 // shared-memory map (bytes): B operands as K-major SWIZZLE_NONE panels, offset(row, k) = (k/4)*rows*16 + row*16 + (k%4)*4
@@ -109,6 +110,110 @@ __device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[16]
 __device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+// bit j of the result: x[j] > 0 for 32 floats of one saved activation row
+__device__ __forceinline__ uint32_t relu_mask32(const float* __restrict__ row, bool ok) {
+    uint32_t m = 0;
+    if (ok) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(row) + q);
+            m |= (uint32_t)((t.x > 0.f) | ((t.y > 0.f) << 1) | ((t.z > 0.f) << 2) | ((t.w > 0.f) << 3)) << (4 * q);
+        }
+    }
+    return m;
+}
+
+
+// ---- coalesced row I/O ---------------------------------------------------------------------------------------------
+// A thread owns a ROW (its TMEM lane), so `store16(dst + row * ld, v)` makes one instruction touch 32 different lines:
+// ncu showed the L1 data pipe 71-74 % busy with such wavefronts in both kernels (34 M store sectors for 503 MB in the
+// forward) while DRAM sat at 31-35 %.  With EMER_CHAIN_STAGE each epilogue warp owns a 32 x 16-float tile in shared
+// memory: rows go in one per lane and come out 8 rows x 64 bytes per instruction (a quarter of the lines per
+// instruction); saved activations come IN 4 rows x 128 bytes per instruction and only their sign bits are exchanged.
+// Row stride 80 B: 8 consecutive lanes hit 8 different 16-byte bank groups both as "lane = row" and as "8 lanes = one
+// 16-byte piece of 8 rows".
+#ifndef EMER_CHAIN_STAGE
+#define EMER_CHAIN_STAGE 1
+#endif
+constexpr int STG_LD = 20;
+constexpr int STG_BYTES = 32 * STG_LD * 4;                 // per epilogue warp
+constexpr int STG_TOTAL = (EPI_THREADS / 32) * STG_BYTES;
+
+// v = 16 columns of this lane's row; dst = address of (the warp's first row, first of the 16 columns)
+__device__ __forceinline__ void put16(float* stg, int lane, const float (&v)[16], float* dst, int64_t ld, int rows_valid) {
+    if (stg == nullptr) {
+        if (lane < rows_valid) store16(dst + (int64_t)lane * ld, v);
+        return;
+    }
+    __syncwarp();                                            // the tile's previous use is over
+    float* mine = stg + lane * STG_LD;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(mine + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    __syncwarp();
+    const int rr = lane & 7, q = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + rr;
+        const float4 t = *reinterpret_cast<const float4*>(stg + r * STG_LD + q * 4);
+        if (r < rows_valid) *reinterpret_cast<float4*>(dst + (int64_t)r * ld + q * 4) = t;
+    }
+}
+
+// 8 columns (the last product's rows are k_enc wide: 8-column chunks)
+__device__ __forceinline__ void put8(float* stg, int lane, const float (&v)[8], float* dst, int64_t ld, int rows_valid) {
+    if (stg == nullptr) {
+        if (lane < rows_valid) {
+            float* d = dst + (int64_t)lane * ld;
+            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        return;
+    }
+    __syncwarp();
+    float* mine = stg + lane * STG_LD;
+    *reinterpret_cast<float4*>(mine) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(mine + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    __syncwarp();
+    const int rr = lane & 15, q = lane >> 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = i * 16 + rr;
+        const float4 t = *reinterpret_cast<const float4*>(stg + r * STG_LD + q * 4);
+        if (r < rows_valid) *reinterpret_cast<float4*>(dst + (int64_t)r * ld + q * 4) = t;
+    }
+}
+
+// bit j of the result: x[j] > 0 for the 32 floats at src + lane * ld (src = the warp's first row).  Staged form: the warp
+// reads 4 rows x 128 B per instruction, every lane turns its 16-byte piece into 4 sign bits, and the row's owner collects
+// its 8 nibbles from shared memory.
+__device__ __forceinline__ uint32_t get_mask32(float* stg, int lane, const float* __restrict__ src, int64_t ld, int rows_valid) {
+    if (stg == nullptr) return relu_mask32(src + (int64_t)lane * ld, lane < rows_valid);
+    uint8_t* nib = reinterpret_cast<uint8_t*>(stg);         // [32 rows][8 pieces]
+    const int piece = lane & 7, r0 = lane >> 3;
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + r0;
+        t[i] = r < rows_valid ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * ld) + piece) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + r0;
+        nib[r * 8 + piece] = (uint8_t)((t[i].x > 0.f) | ((t[i].y > 0.f) << 1) | ((t[i].z > 0.f) << 2) | ((t[i].w > 0.f) << 3));
+    }
+    __syncwarp();
+    const uint2 b = *reinterpret_cast<const uint2*>(nib + lane * 8);
+    // bytes b0..b7 hold one nibble each: mask = sum nibble_p << 4p
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        m |= ((b.x >> (8 * k)) & 0xFu) << (4 * k);
+        m |= ((b.y >> (8 * k)) & 0xFu) << (16 + 4 * k);
+    }
+    return m;
 }
 
 template <int K_ENC>
@@ -213,6 +318,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
         const int wg = tid >> 8;                 // tile slot
         const int half = (tid >> 7) & 1;         // column half
         const int r_in = tid & 127;
+        const int lane = tid & 31;
+        float* stg = p.stg_off ? reinterpret_cast<float*>(smem + p.stg_off + warp * STG_BYTES) : nullptr;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(wg * 256);
         const uint32_t a_lo = a_hi + 64u;
@@ -240,6 +347,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
             const int64_t row = tile * ROWS + r_in;
             const bool row_ok = row < p.n;
             const int64_t ray = (row_ok ? row : (p.n - 1)) / p.samples;
+            const int64_t wrow0 = tile * ROWS + (r_in & ~31);                 // the warp's first row
+            const int rows_valid = (int)(p.n - wrow0 < 32 ? (p.n - wrow0 < 0 ? 0 : p.n - wrow0) : 32);
 
             // ---- stage 0 operand: enc row -> tf32 hi / lo in TMEM
 #pragma unroll
@@ -275,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + bb0_s[c * 16 + j], 0.0f);
-                if (p.save_hb && row_ok) store16(p.save_hb + row * H + c * 16, v);
+                if (p.save_hb) put16(stg, lane, v, p.save_hb + wrow0 * H + c * 16, H, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -297,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bb1_s[c * 16 + j];
                 if (c == 0 && row_ok) p.sigma[row] = expf(v[0] - 1.0f);
-                if (p.save_hg && row_ok) store16(p.save_hg + row * 128 + H + c * 16, v);
+                if (p.save_hg) put16(stg, lane, v, p.save_hg + wrow0 * 128 + H + c * 16, 128, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -312,7 +421,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bb1_s[c * 16 + j];
-                    if (p.save_sem && row_ok) store16(p.save_sem + row * H + (c - 4) * 16, v);
+                    if (p.save_sem) put16(stg, lane, v, p.save_sem + wrow0 * H + (c - 4) * 16, H, rows_valid);
                 }
             }
             tmem_st_wait();
@@ -337,7 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + b[j], 0.0f);
-                if (p.save_hg && row_ok) store16(p.save_hg + row * 128 + c * 16, v);
+                if (p.save_hg) put16(stg, lane, v, p.save_hg + wrow0 * 128 + c * 16, 128, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -364,7 +473,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r[j]) + b[j], 0.0f);
-                if (p.save_h1 && row_ok) store16(p.save_h1 + row * H + c * 16, v);
+                if (p.save_h1) put16(stg, lane, v, p.save_h1 + wrow0 * H + c * 16, H, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -417,6 +526,7 @@ struct BwdParams {
     float *dz2, *dz1, *d1, *dzb, *d_enc; int64_t ld_denc;            // [N,3], [N,64], [N,128] = [dZ0 | dF], [N,64], [N, k_enc]
     float* d_ray_bias; int samples;                                  // [R,128] += ; ray sums only when samples % 32 == 0
     int64_t n;
+    int stg_off;                                                     // staging tiles (see put16), 0 = none
 };
 
 struct BSmem {
@@ -453,19 +563,6 @@ __device__ __forceinline__ void stage_weight_t(uint8_t* hi, uint8_t* lo, const f
         *reinterpret_cast<float*>(lo + off) = l;
     }
     (void)kpad;
-}
-
-// bit j of the result: x[j] > 0 for 32 floats of one saved activation row
-__device__ __forceinline__ uint32_t relu_mask32(const float* __restrict__ row, bool ok) {
-    uint32_t m = 0;
-    if (ok) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(row) + q);
-            m |= (uint32_t)((t.x > 0.f) | ((t.y > 0.f) << 1) | ((t.z > 0.f) << 2) | ((t.w > 0.f) << 3)) << (4 * q);
-        }
-    }
-    return m;
 }
 
 // Column sums over the 32 lanes of a warp of v[16] (recursive halving: 15 + 1 shuffles).  Afterwards every lane holds the
@@ -599,6 +696,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
         const uint32_t a_lo = a_hi + 64u;
         const uint32_t d_addr = a_hi + 128u;
         const bool ray_sums = p.d_ray_bias != nullptr && (p.samples % 32 == 0);
+        float* stg = p.stg_off ? reinterpret_cast<float*>(smem + p.stg_off + warp * STG_BYTES) : nullptr;
         uint32_t ph = 0;
 
         for (int it = 0; it < iters; ++it) {
@@ -606,10 +704,11 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             if (tile >= n_tiles) break;
             const int64_t row = tile * ROWS + r_in;
             const bool row_ok = row < p.n;
-            const int64_t rsafe = row_ok ? row : 0;
+            const int64_t wrow0 = tile * ROWS + (r_in & ~31);                 // the warp's first row
+            const int rows_valid = (int)(p.n - wrow0 < 32 ? (p.n - wrow0 < 0 ? 0 : p.n - wrow0) : 32);
             // the warp's 32 rows belong to one ray (samples % 32 == 0); rows past the end contribute zeros
-            const int64_t ray = (tile * ROWS + (r_in & ~31)) / p.samples;
-            const bool warp_live = tile * ROWS + (r_in & ~31) < p.n;
+            const int64_t ray = wrow0 / p.samples;
+            const bool warp_live = wrow0 < p.n;
 
             // ---- stage 0 operand: dZ2 = d_rgb * rgb (1 - rgb), 3 columns of an 8-wide k step (written by half 0)
             if (half == 0) {
@@ -636,7 +735,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 0 result: dZ1 = dH1 * (h1 > 0)
-            uint32_t mask = relu_mask32(p.h1 + rsafe * H + half * 32, row_ok);        // columns 32 half .. 32 half + 31
+            uint32_t mask = get_mask32(stg, lane, p.h1 + wrow0 * H + half * 32, H, rows_valid);   // columns 32 half .. 32 half + 31
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
@@ -647,7 +746,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = ((mask >> ((c & 1) * 16 + j)) & 1u) ? __uint_as_float(r[j]) : 0.0f;
-                if (row_ok) store16(p.dz1 + row * H + c * 16, v);
+                put16(stg, lane, v, p.dz1 + wrow0 * H + c * 16, H, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -663,7 +762,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             mbar_arrive_warp(&a_full[wg]);
 
             // ---- stage 1 result: dZ0 = dH0 * (h0 > 0)   (dG stays in the accumulator's upper half)
-            mask = relu_mask32(p.hg + rsafe * 128 + half * 32, row_ok);
+            mask = get_mask32(stg, lane, p.hg + wrow0 * 128 + half * 32, 128, rows_valid);
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
@@ -674,7 +773,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = ((mask >> ((c & 1) * 16 + j)) & 1u) ? __uint_as_float(r[j]) : 0.0f;
-                if (row_ok) store16(p.d1 + row * 128 + c * 16, v);
+                put16(stg, lane, v, p.d1 + wrow0 * 128 + c * 16, 128, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -713,7 +812,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + g[j];
                 if (c == 0) v[0] += ds;
-                if (row_ok) store16(p.d1 + row * 128 + H + c * 16, v);
+                put16(stg, lane, v, p.d1 + wrow0 * 128 + H + c * 16, 128, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -750,7 +849,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             }
 
             // ---- stage 3 result: dZb = dHb * (hb > 0)
-            mask = relu_mask32(p.hb + rsafe * H + half * 32, row_ok);
+            mask = get_mask32(stg, lane, p.hb + wrow0 * H + half * 32, H, rows_valid);
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
 #pragma unroll
@@ -761,7 +860,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = ((mask >> ((c & 1) * 16 + j)) & 1u) ? __uint_as_float(r[j]) : 0.0f;
-                if (row_ok) store16(p.dzb + row * H + c * 16, v);
+                put16(stg, lane, v, p.dzb + wrow0 * H + c * 16, H, rows_valid);
                 uint32_t hi[16], lo[16];
                 split16(v, hi, lo);
                 tmem_st16(a_hi + (uint32_t)(c * 16), hi);
@@ -775,21 +874,21 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
             mbar_wait(&d_full[wg], ph); ph ^= 1u;
             tc_fence_after();
             if (p.d_enc) {
+                // half 0 takes the first ceil(nc / 2) 8-column chunks, half 1 the rest (contiguous ranges per thread)
+                constexpr int NC = K_ENC / 8, C_SPLIT = (NC + 1) / 2;
 #pragma unroll
-                for (int c = half; c < K_ENC / 8; c += 2) {
+                for (int c = 0; c < NC; ++c) {
+                    if ((c < C_SPLIT) != (half == 0)) continue;
                     uint32_t r[8];
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                                  : "r"(d_addr + (uint32_t)(c * 8))
                                  : "memory");
                     tmem_ld_wait();
-                    if (row_ok) {
-                        float* dst = p.d_enc + row * p.ld_denc + c * 8;
-                        *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]),
-                                                                      __uint_as_float(r[2]), __uint_as_float(r[3]));
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]),
-                                                                          __uint_as_float(r[6]), __uint_as_float(r[7]));
-                    }
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+                    put8(stg, lane, v, p.d_enc + wrow0 * p.ld_denc + c * 8, p.ld_denc, rows_valid);
                 }
             }
             tc_fence_before();
@@ -828,8 +927,14 @@ extern "C" int emer_field_fwd(const float* enc, int64_t ld_enc, int k_enc, const
     p.ray_bias = ray_bias; p.samples = samples; p.sigma = sigma; p.rgb = rgb;
     p.save_hb = save_hb; p.save_hg = save_hg; p.save_h1 = save_h1; p.save_sem = save_sem; p.n = n;
     const Smem m = smem_map(k_enc, n_feat);
-    const size_t smem = (size_t)m.total;
+    size_t smem = (size_t)m.total;
     EMER_REQUIRE(smem <= 227 * 1024, "emer_field_fwd: %zu B of shared memory needed", smem);
+#if EMER_CHAIN_STAGE
+    {   // staging tiles for coalesced row stores, when they fit beside the weights (n_feat = 64: 157 + 40 KB)
+        const size_t off = (smem + 127) / 128 * 128;
+        if (off + STG_TOTAL <= 227 * 1024) { p.stg_off = (int)off; smem = off + STG_TOTAL; }
+    }
+#endif
     const int64_t n_tiles = ceil_div(n, ROWS);
     int64_t grid = sm_count();
     if (grid > ceil_div(n_tiles, 2)) grid = ceil_div(n_tiles, 2);
@@ -880,8 +985,14 @@ extern "C" int emer_field_bwd(const float* d_rgb, const float* rgb, const float*
     p.dz2 = dz2; p.dz1 = dz1; p.d1 = d1; p.dzb = dzb; p.d_enc = d_enc; p.ld_denc = ld_denc; p.d_ray_bias = d_ray_bias; p.samples = samples;
     p.n = n;
     const BSmem m = bsmem_map(k_enc, n_feat);
-    const size_t smem = (size_t)m.total;
+    size_t smem = (size_t)m.total;
     EMER_REQUIRE(smem <= 227 * 1024, "emer_field_bwd: %zu B of shared memory needed", smem);
+#if EMER_CHAIN_STAGE
+    {
+        const size_t off = (smem + 127) / 128 * 128;
+        if (off + STG_TOTAL <= 227 * 1024) { p.stg_off = (int)off; smem = off + STG_TOTAL; }
+    }
+#endif
     const int64_t n_tiles = ceil_div(n, ROWS);
     int64_t grid = sm_count();
     if (grid > ceil_div(n_tiles, 2)) grid = ceil_div(n_tiles, 2);
