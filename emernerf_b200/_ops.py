@@ -701,6 +701,8 @@ class _FieldChain(torch.autograd.Function):
         _need_cuda(enc, ray_bias, wb0, wb1, w0, w1, w2)
         enc2, ld_enc = _rows(enc, enc.shape[-1])
         n, k_enc = enc2.shape
+        if ld_enc % 8 or enc2.data_ptr() % 32:          # the kernel reads its rows 32 bytes at a time
+            enc2, ld_enc = enc2.contiguous(), k_enc
         n_feat = wb1.shape[0]
         n_ray_cols = w0.shape[1] - 64                   # [dir | emb] columns in front of geo (radiance_field.py:647)
         ws = [_f32c(t) for t in (wb0, bb0, wb1, bb1, w0, w1, w2, b2)]

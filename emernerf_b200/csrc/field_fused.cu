@@ -107,9 +107,23 @@ __device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[16]
     }
 }
 
+// 256-bit global accesses (sm_100: LDG / STG .256).  A thread owns a ROW here (its TMEM lane), so every 16-byte access of a
+// warp lands in a different 32-byte sector and the L1 data pipe -- one wavefront per sector -- was 71-74 % busy in both
+// kernels with HALF-used sectors (34 M store sectors for 503 MB in the forward, profiles/r2_chain_ncu_summary.md).
+// 32 bytes per instruction fills a sector per wavefront: half the wavefronts, no staging latency.  Addresses must be
+// 32-byte aligned (the entry points check the buffers; row strides and column offsets are multiples of 8 floats).
+__device__ __forceinline__ void st8(float* dst, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6), "f"(a7) : "memory");
+}
+__device__ __forceinline__ void ld8(const float* src, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(src));
+}
+
 __device__ __forceinline__ void store16(float* dst, const float (&v)[16]) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    st8(dst, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    st8(dst + 8, v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
 }
 
 // bit j of the result: x[j] > 0 for 32 floats of one saved activation row
@@ -117,25 +131,25 @@ __device__ __forceinline__ uint32_t relu_mask32(const float* __restrict__ row, b
     uint32_t m = 0;
     if (ok) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(row) + q);
-            m |= (uint32_t)((t.x > 0.f) | ((t.y > 0.f) << 1) | ((t.z > 0.f) << 2) | ((t.w > 0.f) << 3)) << (4 * q);
+        for (int q = 0; q < 4; ++q) {
+            float t[8];
+            ld8(row + 8 * q, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m |= (uint32_t)(t[j] > 0.f) << (8 * q + j);
         }
     }
     return m;
 }
 
-
-// ---- coalesced row I/O ---------------------------------------------------------------------------------------------
-// A thread owns a ROW (its TMEM lane), so `store16(dst + row * ld, v)` makes one instruction touch 32 different lines:
-// ncu showed the L1 data pipe 71-74 % busy with such wavefronts in both kernels (34 M store sectors for 503 MB in the
-// forward) while DRAM sat at 31-35 %.  With EMER_CHAIN_STAGE each epilogue warp owns a 32 x 16-float tile in shared
-// memory: rows go in one per lane and come out 8 rows x 64 bytes per instruction (a quarter of the lines per
-// instruction); saved activations come IN 4 rows x 128 bytes per instruction and only their sign bits are exchanged.
+// ---- coalesced row I/O through shared memory (EMER_CHAIN_STAGE=1; measured, NOT the default) --------------------------
+// Each epilogue warp owns a 32 x 16-float tile in shared memory: rows go in one per lane and come out 8 rows x 64 bytes
+// per instruction; saved activations come IN 4 rows x 128 bytes per instruction and only their sign bits are exchanged.
 // Row stride 80 B: 8 consecutive lanes hit 8 different 16-byte bank groups both as "lane = row" and as "8 lanes = one
-// 16-byte piece of 8 rows".
+// 16-byte piece of 8 rows".  A/B on one box (GPU suite green on both): forward 0.315 ms with, 0.260 ms without; backward
+// 0.334 / 0.353 ms -- the two __syncwarp + shared-memory round trips sit on the serial path of every stage, and the
+// data pipe counts SECTORS, which 64-byte pieces only halve.  The 256-bit row accesses above halve them for free.
 #ifndef EMER_CHAIN_STAGE
-#define EMER_CHAIN_STAGE 1
+#define EMER_CHAIN_STAGE 0
 #endif
 constexpr int STG_LD = 20;
 constexpr int STG_BYTES = 32 * STG_LD * 4;                 // per epilogue warp
@@ -164,11 +178,7 @@ __device__ __forceinline__ void put16(float* stg, int lane, const float (&v)[16]
 // 8 columns (the last product's rows are k_enc wide: 8-column chunks)
 __device__ __forceinline__ void put8(float* stg, int lane, const float (&v)[8], float* dst, int64_t ld, int rows_valid) {
     if (stg == nullptr) {
-        if (lane < rows_valid) {
-            float* d = dst + (int64_t)lane * ld;
-            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
+        if (lane < rows_valid) st8(dst + (int64_t)lane * ld, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         return;
     }
     __syncwarp();
@@ -319,7 +329,11 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
         const int half = (tid >> 7) & 1;         // column half
         const int r_in = tid & 127;
         const int lane = tid & 31;
+#if EMER_CHAIN_STAGE
         float* stg = p.stg_off ? reinterpret_cast<float*>(smem + p.stg_off + warp * STG_BYTES) : nullptr;
+#else
+        constexpr float* stg = nullptr;
+#endif
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t a_hi = tmem_base + lane_base + (uint32_t)(wg * 256);
         const uint32_t a_lo = a_hi + 64u;
@@ -328,16 +342,21 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
         const float* bb1_s = bias_s + 64;
         const float* b2_s = bias_s + 192;
         uint32_t ph = 0;
-        constexpr int NQ = K_ENC / 4;
 
-        float4 x_next[NQ];                       // this thread's enc row of the NEXT tile (prefetched)
+        float x_next[K_ENC / 8][8];              // this thread's 8-column chunks of the NEXT tile's enc row (prefetched)
         auto load_enc = [&](int64_t tile) {
             const int64_t row = tile * ROWS + r_in;
             const bool ok = tile < n_tiles && row < p.n;
-            const float4* src = reinterpret_cast<const float4*>(p.enc + (ok ? row : 0) * p.ld_enc);
+            const float* src = p.enc + (ok ? row : 0) * p.ld_enc;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (((q >> 1) & 1) == half) x_next[q] = ok ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < K_ENC / 8; ++c) {
+                if ((c & 1) != half) continue;
+                if (ok) ld8(src + c * 8, x_next[c]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x_next[c][j] = 0.0f;
+                }
+            }
         };
         load_enc((int64_t)blockIdx.x * 2 + wg);
 
@@ -354,13 +373,11 @@ __global__ void __launch_bounds__(THREADS, 1) field_fwd_kernel(const FwdParams p
 #pragma unroll
             for (int c = 0; c < K_ENC / 8; ++c) {
                 if ((c & 1) == half) {
-                    const float4 u0 = x_next[2 * c], u1 = x_next[2 * c + 1];
-                    const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float h, l;
-                        split(v[j], h, l);
+                        split(x_next[c][j], h, l);
                         hi[j] = __float_as_uint(h);
                         lo[j] = __float_as_uint(l);
                     }
@@ -696,7 +713,11 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(const BwdParams p
         const uint32_t a_lo = a_hi + 64u;
         const uint32_t d_addr = a_hi + 128u;
         const bool ray_sums = p.d_ray_bias != nullptr && (p.samples % 32 == 0);
+#if EMER_CHAIN_STAGE
         float* stg = p.stg_off ? reinterpret_cast<float*>(smem + p.stg_off + warp * STG_BYTES) : nullptr;
+#else
+        constexpr float* stg = nullptr;
+#endif
         uint32_t ph = 0;
 
         for (int it = 0; it < iters; ++it) {
@@ -916,10 +937,10 @@ extern "C" int emer_field_fwd(const float* enc, int64_t ld_enc, int k_enc, const
     EMER_REQUIRE(k_enc == 32 || k_enc == 40 || k_enc == 64, "emer_field_fwd: k_enc=%d (L*F of the grid) must be 32, 40 or 64", k_enc);
     EMER_REQUIRE(n_feat == 64 || n_feat == 128, "emer_field_fwd: n_feat=%d must be 64 or 128", n_feat);
     EMER_REQUIRE(samples > 0, "emer_field_fwd: samples per ray must be positive");
-    EMER_REQUIRE(ld_enc % 4 == 0 && ((uintptr_t)enc & 15) == 0, "emer_field_fwd: enc rows must be 16-byte aligned");
+    EMER_REQUIRE(ld_enc % 8 == 0 && ((uintptr_t)enc & 31) == 0, "emer_field_fwd: enc rows must be 32-byte aligned (256-bit row loads)");
     EMER_REQUIRE(((uintptr_t)ray_bias & 15) == 0, "emer_field_fwd: ray_bias must be 16-byte aligned");
-    EMER_REQUIRE((((uintptr_t)save_hb | (uintptr_t)save_hg | (uintptr_t)save_h1 | (uintptr_t)save_sem) & 15) == 0,
-                 "emer_field_fwd: save buffers must be 16-byte aligned");
+    EMER_REQUIRE((((uintptr_t)save_hb | (uintptr_t)save_hg | (uintptr_t)save_h1 | (uintptr_t)save_sem) & 31) == 0,
+                 "emer_field_fwd: save buffers must be 32-byte aligned");
     EMER_REQUIRE(n_feat == 64 || save_sem, "emer_field_fwd: the semantic half needs its output buffer");
     FwdParams p{};
     p.enc = enc; p.ld_enc = ld_enc; p.k_enc = k_enc; p.wb0 = wb0; p.bb0 = bb0; p.wb1 = wb1; p.bb1 = bb1; p.n_feat = n_feat;
@@ -973,10 +994,10 @@ extern "C" int emer_field_bwd(const float* d_rgb, const float* rgb, const float*
     EMER_REQUIRE(k_enc == 32 || k_enc == 40 || k_enc == 64, "emer_field_bwd: k_enc=%d must be 32, 40 or 64", k_enc);
     EMER_REQUIRE(n_feat == 64 || n_feat == 128, "emer_field_bwd: n_feat=%d must be 64 or 128", n_feat);
     EMER_REQUIRE(samples > 0, "emer_field_bwd: samples per ray must be positive");
-    EMER_REQUIRE(!d_enc || (ld_denc % 4 == 0 && ld_denc >= k_enc), "emer_field_bwd: d_enc rows must be 16-byte aligned");
+    EMER_REQUIRE(!d_enc || (ld_denc % 8 == 0 && ld_denc >= k_enc), "emer_field_bwd: d_enc rows must be 32-byte aligned");
     EMER_REQUIRE((((uintptr_t)hb | (uintptr_t)hg | (uintptr_t)h1 | (uintptr_t)dz1 | (uintptr_t)d1 | (uintptr_t)dzb |
-                   (uintptr_t)d_enc | (uintptr_t)d_geo | (uintptr_t)d_sem) & 15) == 0,
-                 "emer_field_bwd: row buffers must be 16-byte aligned");
+                   (uintptr_t)d_enc | (uintptr_t)d_geo | (uintptr_t)d_sem) & 31) == 0,
+                 "emer_field_bwd: row buffers must be 32-byte aligned (256-bit row accesses)");
     EMER_REQUIRE(!d_ray_bias || samples % 32 == 0, "emer_field_bwd: per-ray sums need samples %% 32 == 0 (got %d)", samples);
     BwdParams p{};
     p.d_rgb = d_rgb; p.rgb = rgb; p.d_sigma = d_sigma; p.sigma = sigma; p.d_geo = d_geo; p.d_sem = d_sem;

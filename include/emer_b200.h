@@ -190,7 +190,8 @@ int emer_linear_tc_bwd_weight_mn(const float* x, int64_t ldx, const float* dz, i
  *      activations in tensor memory.  Replaces the chain of nn.Linear / torch.cat / trunc_exp / sigmoid calls of
  *      radiance_fields/radiance_field.py:74-80,314-318 (base_mlp), :422 (density), :131-143,622-658 (query_rgb) and
  *      radiance_fields/mlp.py:38-46 for one block of hash-grid features.
- *   enc[N, k_enc] (k_enc = 32, 40 or 64; rows 16-byte aligned)
+ *   enc[N, k_enc] (k_enc = 32, 40 or 64; rows 32-byte aligned: ld_enc % 8 == 0 -- the kernel moves rows 256 bits at a time,
+ *   and so must be the save buffers)
  *   feats = relu(enc wb0^T + bb0) wb1^T + bb1        wb0 [64, k_enc], wb1 [n_feat, 64], n_feat = 64 | 128
  *   sigma[n] = exp(feats[n, 0] - 1)
  *   h0 = relu(geo w0g^T + ray_bias[ray, 0:64]),  h1 = relu(h0 w1h^T + geo w1g^T + ray_bias[ray, 64:128]),
@@ -214,7 +215,8 @@ int emer_field_fwd(const float* enc, int64_t ld_enc, int k_enc, const float* wb0
  *   dzb[N,64] = (dF wb1[:64] + d_sem wb1[64:]) * (hb > 0);  d_enc[N, k_enc] = dzb wb0   (row stride ld_denc)
  *   d_ray_bias[R,128] += per-ray sums of [dz0 | dz1]   (caller zeroes; needs samples % 32 == 0; may be NULL)
  * hb / hg / h1 / rgb / sigma are emer_field_fwd's saves and outputs.  d_rgb, d_sigma, d_geo, d_sem, d_enc, dz2 may be
- * NULL.  The weight gradients are X^T dZ products over dz2 / dz1 / d1 / dzb (emer_linear_tc_bwd_weight). */
+ * NULL.  Row buffers 32-byte aligned, ld_denc % 8 == 0.  The weight gradients are X^T dZ products over dz2 / dz1 / d1 /
+ * dzb (emer_linear_tc_bwd_weight_mn). */
 int emer_field_bwd(const float* d_rgb, const float* rgb, const float* d_sigma, const float* sigma,
                    const float* d_geo, const float* d_sem, const float* hb, const float* hg, const float* h1,
                    const float* wb0, int k_enc, const float* wb1, int n_feat, const float* w0g, int64_t ld_w0,

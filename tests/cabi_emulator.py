@@ -39,6 +39,10 @@ def _aligned16(*ptrs) -> bool:
     return all(_addr(p) % 16 == 0 for p in ptrs)
 
 
+def _aligned32(*ptrs) -> bool:
+    return all(_addr(p) % 32 == 0 for p in ptrs)
+
+
 def _view(ptr, rows: int, cols: int, ld=None, ctype=ctypes.c_float, dtype=np.float32):
     """[rows, cols] tensor aliasing the caller's memory at ``ptr`` with row stride ``ld`` (elements)."""
     addr = _addr(ptr)
@@ -498,8 +502,8 @@ def emer_field_fwd(enc, ld_enc, k_enc, wb0, bb0, wb1, bb1, n_feat, w0g, ld_w0, w
     _require(k_enc in (32, 40, 64), f"emer_field_fwd: k_enc={k_enc} (L*F of the grid) must be 32, 40 or 64")
     _require(n_feat in (64, 128), f"emer_field_fwd: n_feat={n_feat} must be 64 or 128")
     _require(samples > 0, "emer_field_fwd: samples per ray must be positive")
-    _require(ld_enc % 4 == 0 and _aligned16(enc, ray_bias, save_hb, save_hg, save_h1, save_sem),
-             "emer_field_fwd: rows must be 16-byte aligned")
+    _require(ld_enc % 8 == 0 and _aligned32(enc, save_hb, save_hg, save_h1, save_sem) and _aligned16(ray_bias),
+             "emer_field_fwd: rows must be 32-byte aligned")
     _require(n_feat == 64 or _addr(save_sem), "emer_field_fwd: the semantic half needs its output buffer")
     if n == 0:
         return
@@ -527,8 +531,8 @@ def emer_field_fwd(enc, ld_enc, k_enc, wb0, bb0, wb1, bb1, n_feat, w0g, ld_w0, w
 def emer_field_bwd(d_rgb, rgb, d_sigma, sigma, d_geo, d_sem, hb, hg, h1, wb0, k_enc, wb1, n_feat, w0g, ld_w0, w1h, w1g,
                    ld_w1, w2, dz2, dz1, d1, dzb, d_enc, ld_denc, d_ray_bias, samples, n, stream):
     _require(k_enc in (32, 40, 64) and n_feat in (64, 128) and samples > 0, "emer_field_bwd: bad shape")
-    _require(not _addr(d_enc) or (ld_denc % 4 == 0 and ld_denc >= k_enc), "emer_field_bwd: d_enc rows must be 16-byte aligned")
-    _require(_aligned16(hb, hg, h1, dz1, d1, dzb, d_enc, d_geo, d_sem), "emer_field_bwd: row buffers must be 16-byte aligned")
+    _require(not _addr(d_enc) or (ld_denc % 8 == 0 and ld_denc >= k_enc), "emer_field_bwd: d_enc rows must be 32-byte aligned")
+    _require(_aligned32(hb, hg, h1, dz1, d1, dzb, d_enc, d_geo, d_sem), "emer_field_bwd: row buffers must be 32-byte aligned")
     _require(not _addr(d_ray_bias) or samples % 32 == 0, "emer_field_bwd: per-ray sums need samples % 32 == 0")
     if n == 0:
         return
