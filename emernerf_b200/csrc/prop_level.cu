@@ -214,16 +214,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) prop_level_kernel(const PropPar
 #pragma unroll 4
             for (int j = 0; j < PL_HID; ++j) {
                 float h = b0s[j];
-                if constexpr (LF_T > 0 && LF_T % 4 == 0) {
-                    // one 16-byte shared-memory load per 4 weights (broadcast), same fma chain
-                    float wr[LF_T];
-                    pl_load_row<LF_T>(w0s + j * LF_T, wr);
 #pragma unroll
-                    for (int i = 0; i < LF_T; ++i) h = fmaf(wr[i], enc[i], h);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < LF; ++i) h = fmaf(w0s[j * LF + i], enc[i], h);
-                }
+                for (int i = 0; i < LF; ++i) h = fmaf(w0s[j * LF + i], enc[i], h);
                 h = h > 0.0f ? h : 0.0f;
                 raw = fmaf(w1s[j], h, raw);
             }
