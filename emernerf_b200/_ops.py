@@ -646,6 +646,10 @@ class _FieldTail(torch.autograd.Function):
         if d_rgb_in is None:
             g2 = torch.zeros((n, ld), dtype=torch.float32, device=f2.device)
         else:
+            # INVARIANT: the kernel adds d_sigma's contribution to column 0 of this buffer IN PLACE.  rgb_in has exactly one
+            # consumer (mlp_chain, whose backward hands over a buffer it allocated for this purpose and never reads
+            # again), so nothing else can observe the mutation; a tensor hook or retain_grad() on rgb_in would see the
+            # combined gradient.  field_tail() is not exported for other uses.
             g2 = d_rgb_in.reshape(n, width)
             if g2.stride(1) != 1 or g2.stride(0) % 4 != 0 or g2.data_ptr() % 16 != 0:
                 g2 = torch.nn.functional.pad(g2, (0, ld - width))
