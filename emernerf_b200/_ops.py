@@ -98,13 +98,7 @@ def _grad_sink(t: Optional[Tensor]):
         return None
     touched = getattr(on_touch, "__self__", None)
     is_touched = (lambda: id(p) in touched._touched) if hasattr(touched, "_touched") else None
-
-    def touch():
-        if _SIDE_ACTIVE[0]:
-            _SIDE_PARAM_IDS.add(id(p))           # this gradient is being written on a side stream (see side_touched)
-        on_touch(p)
-
-    return sink, touch, is_touched
+    return sink, (lambda: on_touch(p)), is_touched
 
 
 # ----------------------------------------------------------------------------- weight gradients on a side stream
@@ -118,8 +112,6 @@ WGRAD_STREAM = os.environ.get("EMER_WGRAD_STREAM", "1") == "1"
 PROP_TRAIN = os.environ.get("EMER_PROP_TRAIN", "fused")
 _SIDE: Dict[int, "torch.cuda.Stream"] = {}
 _PENDING: Dict[int, bool] = {}
-_SIDE_ACTIVE = [0]              # > 0 while launches go to a side stream
-_SIDE_PARAM_IDS: set = set()    # parameters whose gradient sink was written there since the last join
 _AFTER_JOIN: list = []          # small updates of buffers the main stream also writes: run there, after the join
 
 
@@ -139,13 +131,11 @@ class _on_side_stream:
         for t in self.tensors:
             t.record_stream(side)
         _PENDING[idx] = True
-        _SIDE_ACTIVE[0] += 1
         self.ctx = torch.cuda.stream(side)
         self.ctx.__enter__()
         return side
 
     def __exit__(self, *exc):
-        _SIDE_ACTIVE[0] -= 1
         return self.ctx.__exit__(*exc)
 
 
@@ -167,13 +157,6 @@ def join_side_streams() -> None:
             _PENDING[idx] = False
     while _AFTER_JOIN:
         _AFTER_JOIN.pop(0)()
-    _SIDE_PARAM_IDS.clear()
-
-
-def side_touched(param) -> bool:
-    """Whether ``param``'s gradient is (still) being produced on a side stream: the optimizer may update every other
-    parameter group before it joins."""
-    return id(param) in _SIDE_PARAM_IDS
 
 
 def _f32c(t: Tensor) -> Tensor:

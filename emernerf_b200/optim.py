@@ -20,7 +20,6 @@ with the reference's own torch optimizer nothing here is active and the ordinary
 from __future__ import annotations
 
 import ctypes
-import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -142,54 +141,37 @@ class FusedAdam(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ the step
     @torch.no_grad()
-    def _update_group(self, group, g, active) -> None:
-        if group["lr"] != g.lr_host:
-            g.hyper[1].fill_(group["lr"])
-            g.lr_host = group["lr"]
-        g.hyper[0].add_(1.0)
-        lo, hi = 0, g.total
-        if self.shard is not None:
-            rank, world = self.shard
-            per = g.total // world if g.total % (ALIGN * world) == 0 else (g.total // ALIGN + world - 1) // world * ALIGN
-            lo, hi = min(rank * per, g.total), min((rank + 1) * per, g.total)
-        blocks, prefix, n_blocks, total = g.descriptor(active, lo, hi)
-        beta1, beta2 = group["betas"]
-        _lib.DEVICE = g.grad.device.index
-        _lib.call("emer_adam_step", ctypes.c_void_p(blocks.data_ptr()), ctypes.c_void_p(prefix.data_ptr()), n_blocks, total,
-                  ctypes.c_void_p(g.hyper.data_ptr()), float(beta1), float(beta2), float(group["eps"]),
-                  float(group["weight_decay"]), 1, _ops._stream())
-        if self.shard is not None and hi - lo < g.total:
-            # the part of the gradient this rank did not consume still has to be cleared
-            if lo > 0:
-                g.grad[:lo].zero_()
-            if hi < g.total:
-                g.grad[hi:].zero_()
-
-    @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        # Groups none of whose gradients are still being written on a side stream (the hash tables: their scatter ran on
-        # this stream) are updated first; the join comes before the others, so the table's HBM-bound update runs
-        # beside the tail of the weight-gradient kernels.  EMER_ADAM_EARLY=0: join first, as before.
-        early = os.environ.get("EMER_ADAM_EARLY", "1") == "1"
-        late = []
-        if not early:
-            _ops.join_side_streams()
+        _ops.join_side_streams()                 # weight gradients that ran beside the rest of the backward pass
         for group, g in zip(self.param_groups, self._groups):
             active = tuple(i for i, p in enumerate(g.params) if id(p) in self._touched)
             if not active:
                 continue
-            if early and any(_ops.side_touched(g.params[i]) for i in active):
-                late.append((group, g, active))
-                continue
-            self._update_group(group, g, active)
-        if early:
-            _ops.join_side_streams()             # weight gradients that ran beside the rest of the backward pass
-            for group, g, active in late:
-                self._update_group(group, g, active)
+            if group["lr"] != g.lr_host:
+                g.hyper[1].fill_(group["lr"])
+                g.lr_host = group["lr"]
+            g.hyper[0].add_(1.0)
+            lo, hi = 0, g.total
+            if self.shard is not None:
+                rank, world = self.shard
+                per = g.total // world if g.total % (ALIGN * world) == 0 else (g.total // ALIGN + world - 1) // world * ALIGN
+                lo, hi = min(rank * per, g.total), min((rank + 1) * per, g.total)
+            blocks, prefix, n_blocks, total = g.descriptor(active, lo, hi)
+            beta1, beta2 = group["betas"]
+            _lib.DEVICE = g.grad.device.index
+            _lib.call("emer_adam_step", ctypes.c_void_p(blocks.data_ptr()), ctypes.c_void_p(prefix.data_ptr()), n_blocks, total,
+                      ctypes.c_void_p(g.hyper.data_ptr()), float(beta1), float(beta2), float(group["eps"]),
+                      float(group["weight_decay"]), 1, _ops._stream())
+            if self.shard is not None and hi - lo < g.total:
+                # the part of the gradient this rank did not consume still has to be cleared
+                if lo > 0:
+                    g.grad[:lo].zero_()
+                if hi < g.total:
+                    g.grad[hi:].zero_()
         self._touched.clear()
         return loss
 
